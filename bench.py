@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- NFFT + adjoint nonuniform points/s on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one forward NFFT (mul!(fHat,p,f)) plus one adjoint NFFT (mul!(f,adjoint(p),fHat)) over the
+workload's M nodes.  Workload at every N: BASELINE.json configs[1] -- 3-D N=(128,128,128), M=2^21 uniform
+random nodes, m=3, sigma=2, Float32, Kaiser-Bessel, POLYNOMIAL window (the reference default).  With N GPUs
+the job is ntransforms=N batched transforms sharing the nodes, one transform per rank (batch sharding,
+SURVEY 8e-a: no collective on the data path), so per-GPU work is fixed ("weak" scaling) and
+value = N * 2*M / t_step.
+
+`--impl reference` times the CPU restatement of the reference's default blocked algorithm
+(oracle/cpu_ref.py: C/OpenMP port + pocketfft; NFFT.jl itself cannot run here: no julia binary).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="C2: 3D NFFT N=(128,128,128), M=2^21 random nodes, m=3, sigma=2, Float32",
+                N=(128, 128, 128), M=2 ** 21, m=3, sigma=2.0, T=np.float32)
+METRIC = "NFFT+adjoint nonuniform pts/sec"
+UNIT = "pts/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(D, s, M, gsz, B=1):
+    """coords + int32 permutation + node values + grid, per spread or interp launch"""
+    return D * s * M + 4 * M + 2 * s * M * B + 2 * s * gsz * B
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import nfft_oracle as O
+    from oracle.cpu_ref import CpuRefPlan, lib
+    w = WORKLOAD
+    cores = lib().ref_num_threads()
+    k = O.random_nodes(w["M"], 3, w["T"], seed=1)
+    t0 = time.perf_counter()
+    p = CpuRefPlan(k, w["N"], m=w["m"], sigma=w["sigma"], workers=cores)
+    t_plan = time.perf_counter() - t0
+    f = O.random_complex(w["N"], w["T"], 2)
+    fh = O.random_complex(w["M"], w["T"], 3)
+    for _ in range(args.warmup):
+        p.forward(f); p.adjoint(fh)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        p.forward(f); p.adjoint(fh)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    val = 2 * w["M"] / t
+    cb = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"full workload, {args.steps} steps of forward+adjoint (M=2^21 each); plan {t_plan:.2f}s excluded"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "note": "reference algorithm restated in C/OpenMP + pocketfft (Julia unavailable)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-mode", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 5
+        args.warmup = min(args.warmup, 1)
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import nfft_jl_b200 as nb
+    from oracle import nfft_oracle as O   # only for the synthetic inputs and the cpu_baseline leg
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    w = WORKLOAD
+    N, M, T = w["N"], w["M"], w["T"]
+    k = O.random_nodes(M, 3, T, seed=1)                     # same nodes on every rank (shared by the batch)
+    kd = torch.from_numpy(np.ascontiguousarray(k.T)).cuda()
+    p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"])
+    p.set_kernel_mode(args.kernel_mode)
+    f_h = O.random_complex(N, T, 100 + rank)
+    fh_h = O.random_complex(M, T, 200 + rank)
+    f = p.empty_image(); f.copy_(torch.from_numpy(np.ascontiguousarray(f_h.T)).cuda().permute(2, 1, 0))
+    fh = p.empty_out(); fh.copy_(torch.from_numpy(fh_h).cuda())
+    f_out = p.empty_image()
+    fh_out = p.empty_out()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step():
+        nb.mul_(fh_out, p, f)
+        nb.mul_(f_out, p.adjoint(), fh)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    p.enable_timing(True)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ts = nb.TimingStats()
+    phases = {n: 0.0 for n in ("deconv", "fft", "conv", "conv_adjoint", "fft_adjoint", "deconv_adjoint")}
+    kt = {"spread": 0.0, "interp": 0.0, "memset": 0.0}
+    l0 = p.launch_count()
+    barrier()
+    for s, e in ev:
+        flush.zero_()                                       # L2 flush between timed iterations (untimed)
+        s.record()
+        nb.mul_(fh_out, p, f, timing=ts)
+        nb.mul_(f_out, p.adjoint(), fh, timing=ts)
+        e.record()
+        e.synchronize()
+        for n in phases:
+            phases[n] += getattr(ts, n)
+        for n, v in p.kernel_times().items():
+            kt[n] += v
+    barrier()
+    launches = p.launch_count() - l0
+    clocks = sampler.stop()
+    t_step = sum(s.elapsed_time(e) for s, e in ev) / args.steps * 1e-3
+    tt = torch.tensor([t_step], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_step = float(tt.item())
+    value = world * 2 * M / t_step
+
+    # ---- end-to-end through the public API with pinned HOST buffers (H2D + D2H inside the timed region)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    f_p = np.asfortranarray(pin(np.ascontiguousarray(f_h.T)).T)
+    fh_p = pin(fh_h)
+    fo_p = np.asfortranarray(pin(np.empty(N[::-1], dtype=p.cT)).T)
+    fho_p = pin(np.empty(M, dtype=p.cT))
+    for _ in range(2):
+        nb.mul_(fho_p, p, f_p); nb.mul_(fo_p, p.adjoint(), fh_p)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nb.mul_(fho_p, p, f_p)
+        nb.mul_(fo_p, p.adjoint(), fh_p)
+    barrier()
+    t_e2e = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    csz = 8
+    e2e = {"value": world * 2 * M / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int((np.prod(N) + M) * csz),
+           "d2h_bytes_per_step": int((np.prod(N) + M) * csz), "ms_per_step": t_e2e * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    gsz = int(np.prod(p.Ñ))
+    abytes = algorithmic_bytes(3, 4, M, gsz)
+    t_spread = kt["spread"] / args.steps
+    t_interp = kt["interp"] / args.steps
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh_:
+            traffic = json.load(fh_).get("spread_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_spread_tile3d<float,3> (adjoint gridding)",
+                "achieved": abytes / t_spread / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": abytes / t_spread / 1e9 / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": abytes, "us_per_launch": t_spread * 1e6,
+                "note": "3-D spreading is shared-memory-bound (216 complex RMWs/node); HBM fraction is the contract metric",
+                "interp": {"kernel": "k_interp_tile3d<float,3>", "achieved": abytes / t_interp / 1e9,
+                           "frac": abytes / t_interp / 1e9 / peak, "us_per_launch": t_interp * 1e6}}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "ntransforms": world, "sharding": "batch (one transform per GPU)",
+                   "precompute": "POLYNOMIAL", "blockSize": list(p.params.blockSize),
+                   "l2": "flushed between timed iterations (256 MiB write, untimed)",
+                   "step": "1 forward + 1 adjoint NFFT; value = n_gpus*2*M/t_step"},
+        "forward_pts_per_s": M / sum(phases[n] for n in ("deconv", "fft", "conv")) * args.steps,
+        "adjoint_pts_per_s": M / sum(phases[n] for n in ("conv_adjoint", "fft_adjoint", "deconv_adjoint")) * args.steps,
+        "phases_us": {n: v / args.steps * 1e6 for n, v in phases.items()},
+        "memset_us": kt["memset"] / args.steps * 1e6,
+        "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_ref import CpuRefPlan, lib
+        cores = lib().ref_num_threads()
+        pc = CpuRefPlan(k, N, m=w["m"], sigma=w["sigma"], workers=cores)
+        pc.forward(f_h); pc.adjoint(fh_h)
+        t0 = time.perf_counter()
+        nrep = 5
+        for _ in range(nrep):
+            pc.forward(f_h); pc.adjoint(fh_h)
+        tc = (time.perf_counter() - t0) / nrep
+        out["cpu_baseline"] = {"value": 2 * M / tc, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"full workload, {nrep} steps of forward+adjoint after 1 warm-up",
+                               "ms_per_step": tc * 1e3}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

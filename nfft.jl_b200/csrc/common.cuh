@@ -1,0 +1,195 @@
+// common.cuh -- plan state, error plumbing and device helpers shared by all kernels of
+// libnfftb200.so (B200 / sm_100a).  See DESIGN.md for the data layout in HBM.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nfftb200.h"
+
+#define NFFTB_MAX_D 3
+#define NFFTB_MAX_M 8            // taps per dim = 2m <= 16
+
+// ---------------------------------------------------------------------------------------
+// complex value types
+// ---------------------------------------------------------------------------------------
+template <typename T> struct Cplx;
+template <> struct Cplx<float> { using type = float2; };
+template <> struct Cplx<double> { using type = double2; };
+
+template <typename T> __host__ __device__ inline typename Cplx<T>::type make_c(T a, T b);
+template <> __host__ __device__ inline float2 make_c<float>(float a, float b) { return make_float2(a, b); }
+template <> __host__ __device__ inline double2 make_c<double>(double a, double b) { return make_double2(a, b); }
+
+// ---------------------------------------------------------------------------------------
+// window parameters handed to the kernels by value
+// ---------------------------------------------------------------------------------------
+template <typename T> struct WinDev {
+    int m;             // kernel half width; 2m taps per dimension
+    int mode;          // NFFTB200_FULL / LINEAR / POLYNOMIAL (TENSOR is mapped to POLYNOMIAL)
+    int lin_scale;     // LUTSize / m
+    T b;               // Kaiser-Bessel shape parameter pi*(2-1/sigma) in T
+    const T* poly;     // (2m+1) x 2m, column-major (column = tap)
+    const T* lin;      // LUTSize + 2
+};
+
+struct GeomDev {
+    int D;
+    int Nt[NFFTB_MAX_D];      // oversampled grid (padded with 1)
+    int N[NFFTB_MAX_D];       // image size (padded with 1)
+    int bs[NFFTB_MAX_D];      // tile size (padded with 1)
+    int nb[NFFTB_MAX_D];      // tiles per dim (padded with 1)
+    long long gsz;            // prod(Nt)
+    long long fsz;            // prod(N)
+};
+
+// ---------------------------------------------------------------------------------------
+// the plan (host side)
+// ---------------------------------------------------------------------------------------
+struct nfftb200_plan {
+    int D = 0;
+    int dtype = NFFTB200_F32;
+    int m = 4;
+    double sigma = 2.0;       // effective sigma = Nt[0]/N[0] rounded to T
+    double reltol = 1e-9;
+    double b = 0.0;           // window shape parameter as evaluated in T
+    int precompute = NFFTB200_POLYNOMIAL;
+    int B = 1;                // ntransforms
+    int device = 0;
+    int64_t N[NFFTB_MAX_D] = {1, 1, 1};
+    int64_t Nt[NFFTB_MAX_D] = {1, 1, 1};
+    int64_t bs[NFFTB_MAX_D] = {1, 1, 1};
+    int64_t nb[NFFTB_MAX_D] = {1, 1, 1};
+    int64_t ntiles = 1;
+    int64_t gsz = 1, fsz = 1;
+    int64_t lut_size = 0;
+    int64_t M = 0;
+    bool have_nodes = false;
+    int kernel_mode = 0;
+
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cufftHandle fft = 0;
+    bool have_fft = false;
+
+    // host copies of the tables (double), for get_table and for re-upload
+    std::vector<double> h_hat_inv;   // concatenated over d
+    std::vector<double> h_poly;      // (2m+1)*2m column-major
+    std::vector<double> h_lin;       // LUTSize+2
+
+    // device tables in T
+    void* d_hat_inv = nullptr;
+    void* d_poly = nullptr;
+    void* d_lin = nullptr;
+
+    // device grid: B * gsz complex T  (p.tmpVec)
+    void* d_grid = nullptr;
+
+    // node state (device)
+    void* d_xs = nullptr;            // shifted nodes in sorted order, D x M of T
+    int32_t* d_perm = nullptr;       // sorted position -> original node id
+    int32_t* d_tile_start = nullptr; // ntiles + 1
+    std::vector<int32_t> h_tile_start;  // host copy (tile-aligned sharding, launch ranges)
+    int64_t cap_nodes = 0;
+
+    // sort scratch
+    uint32_t* d_keys[2] = {nullptr, nullptr};
+    int32_t* d_vals[2] = {nullptr, nullptr};
+    uint32_t* d_hist = nullptr;
+    int64_t cap_hist = 0;
+    int* d_flag = nullptr;
+
+    // staging buffers for host-pointer calls
+    void* d_stage_f = nullptr;  int64_t cap_stage_f = 0;     // bytes
+    void* d_stage_h = nullptr;  int64_t cap_stage_h = 0;     // bytes
+    void* d_stage_k = nullptr;  int64_t cap_stage_k = 0;     // bytes
+    void* d_stage_g = nullptr;  int64_t cap_stage_g = 0;     // bytes
+
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double t[7] = {0, 0, 0, 0, 0, 0, 0};
+    int pending = 0;                 // 0 none, 1 forward, 2 adjoint
+    cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // memset | spread kernel | interp kernel
+    int pending_k = 0;               // bit 0: spread events valid, bit 1: interp events valid
+    double tk[4] = {0, 0, 0, 0};     // spread kernel, interp kernel, grid memset, reserved
+
+    int64_t launches = 0;
+    std::string err;
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1, shard_mode = NFFTB200_SHARD_NONE;
+    int64_t node_lo = 0, node_hi = 0;  // sorted-position range owned by this rank (SHARD_NODES)
+    int b_lo = 0, b_hi = 1;            // transform range owned by this rank (SHARD_BATCH)
+    void* d_slab = nullptr; int64_t cap_slab = 0;
+
+    size_t esz() const { return dtype == NFFTB200_F32 ? 4 : 8; }
+};
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+int nfftb_fail(nfftb200_plan* p, int code, const std::string& msg);
+
+#define CUDA_TRY(p, call)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return nfftb_fail((p), e__ == cudaErrorMemoryAllocation ? NFFTB200_OOM         \
+                                                                    : NFFTB200_CUDA_ERROR, \
+                              std::string(#call) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+#define CUFFT_TRY(p, call)                                                                 \
+    do {                                                                                   \
+        cufftResult r__ = (call);                                                          \
+        if (r__ != CUFFT_SUCCESS)                                                          \
+            return nfftb_fail((p), NFFTB200_CUDA_ERROR,                                    \
+                              std::string(#call) + ": cufft error " + std::to_string((int)r__)); \
+    } while (0)
+
+#define ST_TRY(call)                      \
+    do {                                  \
+        int s__ = (call);                 \
+        if (s__ != NFFTB200_OK) return s__; \
+    } while (0)
+
+template <typename T> inline GeomDev make_geom(const nfftb200_plan* p)
+{
+    GeomDev g;
+    g.D = p->D;
+    for (int d = 0; d < NFFTB_MAX_D; d++) {
+        g.Nt[d] = (int)p->Nt[d]; g.N[d] = (int)p->N[d]; g.bs[d] = (int)p->bs[d]; g.nb[d] = (int)p->nb[d];
+    }
+    g.gsz = p->gsz; g.fsz = p->fsz;
+    return g;
+}
+
+template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
+{
+    WinDev<T> w;
+    w.m = p->m;
+    w.mode = (p->precompute == NFFTB200_TENSOR) ? NFFTB200_POLYNOMIAL : p->precompute;
+    w.lin_scale = (int)(p->lut_size / p->m);
+    w.b = (T)p->b;
+    w.poly = (const T*)p->d_poly;
+    w.lin = (const T*)p->d_lin;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage launchers implemented in the .cu files
+// ---------------------------------------------------------------------------------------
+int nfftb_sort_nodes(nfftb200_plan* p, const void* d_k);                       // sort.cu
+int nfftb_deconvolve(nfftb200_plan* p, const void* d_f, void* d_g, int B);      // deconv.cu
+int nfftb_deconvolve_transpose(nfftb200_plan* p, const void* d_g, void* d_f, int B);
+// t_lo/t_hi: half-open range of reference tiles ("blocks") whose nodes are processed
+int nfftb_spread(nfftb200_plan* p, const void* d_fhat, void* d_g, int B, int is_complex,
+                 int64_t t_lo, int64_t t_hi);                                   // spread.cu
+int nfftb_interp(nfftb200_plan* p, const void* d_g, void* d_fhat, int B, int is_complex,
+                 int64_t t_lo, int64_t t_hi);                                   // interp.cu
+int nfftb_build_tables(nfftb200_plan* p);                                       // tables.cpp

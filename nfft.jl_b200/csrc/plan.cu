@@ -1,0 +1,576 @@
+// plan.cu -- the C ABI of libnfftb200.so (include/nfftb200.h): plan life cycle, nodes!, mul! forward /
+// adjoint drivers and the optional AbstractNFFTs operators, mirroring NFFTPlan
+// (/root/reference/src/implementation.jl:16-193) with the FFT delegated to cuFFT.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+int nfftb_comm_exec_adjoint(nfftb200_plan* p, const void* d_fhat, void* d_f);   // comm.cu
+int nfftb_comm_exec_forward(nfftb200_plan* p, const void* d_f, void* d_fhat);
+void nfftb_comm_destroy(nfftb200_plan* p);
+
+static thread_local std::string g_last_error;
+
+int nfftb_fail(nfftb200_plan* p, int code, const std::string& msg)
+{
+    if (p) p->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (dev < 0) return;                      // host-only plan: never touch the CUDA runtime
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure(nfftb200_plan* p, void** ptr, int64_t* cap, int64_t bytes)
+{
+    if (bytes <= *cap) return NFFTB200_OK;
+    if (*ptr) { cudaFree(*ptr); *ptr = nullptr; *cap = 0; }
+    CUDA_TRY(p, cudaMalloc(ptr, (size_t)bytes));
+    *cap = bytes;
+    return NFFTB200_OK;
+}
+
+int upload_table(nfftb200_plan* p, const std::vector<double>& h, void** d)
+{
+    if (*d) { cudaFree(*d); *d = nullptr; }
+    if (h.empty()) return NFFTB200_OK;
+    CUDA_TRY(p, cudaMalloc(d, h.size() * p->esz()));
+    if (p->dtype == NFFTB200_F32) {
+        std::vector<float> t(h.size());
+        for (size_t i = 0; i < h.size(); i++) t[i] = (float)h[i];
+        CUDA_TRY(p, cudaMemcpy(*d, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+        CUDA_TRY(p, cudaMemcpy(*d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    }
+    return NFFTB200_OK;
+}
+
+// reference defaults (src/precomputation.jl:59-77), shrunk in 3-D only when the padded tile would
+// not fit the 227 KB of shared memory the tiled kernels use
+void default_tiles(nfftb200_plan* p)
+{
+    const int D = p->D;
+    for (int d = 0; d < D; d++) {
+        int64_t v = (D == 1) ? 1024 : (D == 2 ? 64 : 16);
+        p->bs[d] = std::min<int64_t>(v, p->Nt[d]);
+    }
+    if (D == 3) {
+        const int64_t csz = 2 * (int64_t)p->esz();
+        auto fits = [&]() {
+            int64_t c = 1;
+            for (int d = 0; d < 3; d++) c *= p->bs[d] + 2 * p->m;
+            return c * csz + 32 * 1024 <= 227 * 1024;
+        };
+        if (!fits()) p->bs[2] = std::min<int64_t>(8, p->Nt[2]);
+        if (!fits()) { p->bs[0] = std::min<int64_t>(8, p->Nt[0]); p->bs[1] = std::min<int64_t>(8, p->Nt[1]); }
+    }
+}
+
+int make_fft(nfftb200_plan* p)
+{
+    int n[3];
+    for (int d = 0; d < p->D; d++) n[d] = (int)p->Nt[p->D - 1 - d];   // column-major -> cuFFT row-major
+    const cufftType ty = p->dtype == NFFTB200_F32 ? CUFFT_C2C : CUFFT_Z2Z;
+    CUFFT_TRY(p, cufftCreate(&p->fft));
+    p->have_fft = true;
+    size_t ws = 0;
+    long long nn[3] = {n[0], n[1], n[2]};
+    CUFFT_TRY(p, cufftMakePlanMany64(p->fft, p->D, nn, nullptr, 1, p->gsz, nullptr, 1, p->gsz, ty, p->B, &ws));
+    CUFFT_TRY(p, cufftSetStream(p->fft, p->stream));
+    return NFFTB200_OK;
+}
+
+int run_fft(nfftb200_plan* p, void* grid, int dir)
+{
+    const int cdir = dir < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;
+    if (p->dtype == NFFTB200_F32)
+        CUFFT_TRY(p, cufftExecC2C(p->fft, (cufftComplex*)grid, (cufftComplex*)grid, cdir));
+    else
+        CUFFT_TRY(p, cufftExecZ2Z(p->fft, (cufftDoubleComplex*)grid, (cufftDoubleComplex*)grid, cdir));
+    p->launches++;
+    return NFFTB200_OK;
+}
+
+void rec(nfftb200_plan* p, int i)
+{
+    if (p->timing) cudaEventRecord(p->ev[i], p->stream);
+}
+
+int stage_in(nfftb200_plan* p, const void* src, int64_t bytes, int where, void** slot, int64_t* cap,
+             const void** out)
+{
+    if (where == NFFTB200_DEVICE) { *out = src; return NFFTB200_OK; }
+    ST_TRY(ensure(p, slot, cap, bytes));
+    CUDA_TRY(p, cudaMemcpyAsync(*slot, src, (size_t)bytes, cudaMemcpyHostToDevice, p->stream));
+    *out = *slot;
+    return NFFTB200_OK;
+}
+
+int stage_out_buf(nfftb200_plan* p, void* dst, int64_t bytes, int where, void** slot, int64_t* cap, void** out)
+{
+    if (where == NFFTB200_DEVICE) { *out = dst; return NFFTB200_OK; }
+    ST_TRY(ensure(p, slot, cap, bytes));
+    *out = *slot;
+    return NFFTB200_OK;
+}
+
+int stage_back(nfftb200_plan* p, void* dst, const void* dsrc, int64_t bytes, int where)
+{
+    if (where == NFFTB200_DEVICE) return NFFTB200_OK;
+    CUDA_TRY(p, cudaMemcpyAsync(dst, dsrc, (size_t)bytes, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    return NFFTB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nfftb200_version(void) { return 100; }
+
+const char* nfftb200_status_string(int s)
+{
+    switch (s) {
+        case NFFTB200_OK: return "ok";
+        case NFFTB200_BAD_NODE_RANGE: return "nodes out of range [-1/2, 1/2]";
+        case NFFTB200_BAD_DIM: return "node dimension does not match plan dimension";
+        case NFFTB200_SIZE_MISMATCH: return "data is not consistent with the plan";
+        case NFFTB200_UNSUPPORTED: return "unsupported option";
+        case NFFTB200_CUDA_ERROR: return "CUDA error";
+        case NFFTB200_NCCL_ERROR: return "NCCL error";
+        case NFFTB200_OOM: return "out of device memory";
+        case NFFTB200_BAD_ARGUMENT: return "bad argument";
+        case NFFTB200_NO_NODES: return "plan has no nodes";
+        default: return "unknown status";
+    }
+}
+
+const char* nfftb200_last_error(nfftb200_plan* p) { return p ? p->err.c_str() : g_last_error.c_str(); }
+
+int nfftb200_accuracy_params(int m_in, double sigma_in, double reltol_in, int* m_out, double* sigma_out,
+                             double* reltol_out)
+{
+    // accuracyParams / reltolToParams / paramsToReltol, AbstractNFFTs/src/misc.jl:44-81
+    int m;
+    double sigma, reltol;
+    auto from_reltol = [](double r, int& mm, double& ss) {
+        const int w = (int)std::ceil(std::log(1.0 / r) / std::log(10.0)) + 1;
+        mm = w / 2;
+        ss = 2.0;
+    };
+    if (reltol_in > 0) {
+        reltol = reltol_in;
+        from_reltol(reltol, m, sigma);
+    } else if (m_in > 0 && sigma_in > 0) {
+        m = m_in; sigma = sigma_in;
+        reltol = std::pow(10.0, -(2.0 * m - 1.0));
+    } else {
+        reltol = 1e-9;
+        from_reltol(reltol, m, sigma);
+    }
+    if (m_out) *m_out = m;
+    if (sigma_out) *sigma_out = sigma;
+    if (reltol_out) *reltol_out = reltol;
+    return NFFTB200_OK;
+}
+
+int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype, int m, double sigma,
+                         int window, int precompute, int ntransforms, const int64_t* block_size, int device)
+{
+    if (!out) return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "out == NULL");
+    *out = nullptr;
+    if (D < 1 || D > NFFTB_MAX_D) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "only D = 1, 2, 3 are supported");
+    if (dtype != NFFTB200_F32 && dtype != NFFTB200_F64) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "dtype");
+    if (window != NFFTB200_KAISER_BESSEL)
+        return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "Window not yet implemented! (only :kaiser_bessel)");
+    if (precompute < NFFTB200_FULL || precompute > NFFTB200_POLYNOMIAL)
+        return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "precompute flag not supported");
+    if (m < 1 || m > NFFTB_MAX_M) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "m must be in 1..8");
+    if (!(sigma >= 1.0)) return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "sigma must be >= 1");
+    if (ntransforms < 1) return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "ntransforms must be >= 1");
+
+    nfftb200_plan* p = new nfftb200_plan();
+    p->D = D; p->dtype = dtype; p->m = m; p->precompute = precompute; p->B = ntransforms; p->device = device;
+    // initParams, src/precomputation.jl:14-29
+    static const int m2K[9] = {1, 3, 7, 9, 14, 17, 20, 23, 24};
+    p->lut_size = ((int64_t)1 << m2K[std::min(m + 1, 9) - 1]) * m;
+    const double sig_T = dtype == NFFTB200_F32 ? (double)(float)sigma : sigma;
+    for (int d = 0; d < D; d++) {
+        if (N[d] < 1) { delete p; return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "N[d] must be >= 1"); }
+        p->N[d] = N[d];
+        p->Nt[d] = ((int64_t)std::ceil(sig_T * (double)N[d]) / 2) * 2;
+        if (p->Nt[d] < 2 * m) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "oversampled grid smaller than the window (Nt < 2m)"); }
+        if (p->Nt[d] > (1 << 30)) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "grid dimension too large"); }
+    }
+    if (dtype == NFFTB200_F32) {
+        const float s = (float)((double)p->Nt[0] / (double)p->N[0]);
+        p->sigma = s;
+        p->b = (double)((float)M_PI * (2.0f - 1.0f / s));       // pi*(2-1/sigma) evaluated in Float32
+    } else {
+        p->sigma = (double)p->Nt[0] / (double)p->N[0];
+        p->b = M_PI * (2.0 - 1.0 / p->sigma);
+    }
+    if (block_size) {
+        for (int d = 0; d < D; d++) {
+            if (block_size[d] < 1) { delete p; return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "blockSize must be >= 1"); }
+            p->bs[d] = block_size[d];
+        }
+    } else {
+        default_tiles(p);
+    }
+    p->ntiles = 1; p->gsz = 1; p->fsz = 1;
+    for (int d = 0; d < D; d++) {
+        p->nb[d] = (p->Nt[d] + p->bs[d] - 1) / p->bs[d];
+        p->ntiles *= p->nb[d];
+        p->gsz *= p->Nt[d];
+        p->fsz *= p->N[d];
+    }
+    if (p->ntiles >= ((int64_t)1 << 31)) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "too many tiles"); }
+    nfftb_build_tables(p);
+    if (device < 0) {   // host-only plan (parameters + tables, for CPU-side checks); every exec call fails
+        *out = p;
+        return NFFTB200_OK;
+    }
+
+    DeviceGuard guard(device);
+    int st = [&]() -> int {
+        CUDA_TRY(p, cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        p->own_stream = true;
+        for (int i = 0; i < 4; i++) CUDA_TRY(p, cudaEventCreate(&p->ev[i]));
+        for (int i = 0; i < 5; i++) CUDA_TRY(p, cudaEventCreate(&p->evk[i]));
+        ST_TRY(upload_table(p, p->h_hat_inv, &p->d_hat_inv));
+        ST_TRY(upload_table(p, p->h_poly, &p->d_poly));
+        ST_TRY(upload_table(p, p->h_lin, &p->d_lin));
+        CUDA_TRY(p, cudaMalloc(&p->d_grid, (size_t)p->gsz * p->B * 2 * p->esz()));
+        CUDA_TRY(p, cudaMalloc(&p->d_tile_start, sizeof(int32_t) * (size_t)(p->ntiles + 1)));
+        CUDA_TRY(p, cudaMalloc(&p->d_flag, sizeof(int)));
+        ST_TRY(make_fft(p));
+        return NFFTB200_OK;
+    }();
+    if (st != NFFTB200_OK) {
+        g_last_error = p->err;
+        nfftb200_destroy(p);
+        return st;
+    }
+    *out = p;
+    return NFFTB200_OK;
+}
+
+int nfftb200_destroy(nfftb200_plan* p)
+{
+    if (!p) return NFFTB200_OK;
+    DeviceGuard guard(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    nfftb_comm_destroy(p);
+    if (p->have_fft) cufftDestroy(p->fft);
+    void* bufs[] = {p->d_hat_inv, p->d_poly, p->d_lin, p->d_grid, p->d_xs, p->d_tile_start, p->d_keys[0],
+                    p->d_keys[1], p->d_vals[0], p->d_vals[1], p->d_hist, p->d_flag, p->d_stage_f,
+                    p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (int i = 0; i < 4; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    for (int i = 0; i < 5; i++) if (p->evk[i]) cudaEventDestroy(p->evk[i]);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return NFFTB200_OK;
+}
+
+int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    if (M < 0 || M >= ((int64_t)1 << 31)) return nfftb_fail(p, NFFTB200_BAD_ARGUMENT, "M out of range");
+    if (p->device < 0) return nfftb_fail(p, NFFTB200_CUDA_ERROR, "host-only plan (device < 0): no CPU fallback exists");
+    DeviceGuard guard(p->device);
+    if (p->timing) cudaEventRecord(p->ev[0], p->stream);
+    p->have_nodes = false;
+    if (M > p->cap_nodes) {
+        void* old[] = {p->d_xs, p->d_keys[0], p->d_keys[1], p->d_vals[0], p->d_vals[1]};
+        for (void* b : old) if (b) cudaFree(b);
+        p->d_xs = nullptr; p->d_keys[0] = p->d_keys[1] = nullptr; p->d_vals[0] = p->d_vals[1] = nullptr;
+        p->cap_nodes = 0;
+        const size_t n = (size_t)std::max<int64_t>(M, 1);
+        CUDA_TRY(p, cudaMalloc(&p->d_xs, n * p->D * p->esz()));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(p, cudaMalloc((void**)&p->d_keys[i], n * 4));
+            CUDA_TRY(p, cudaMalloc((void**)&p->d_vals[i], n * 4));
+        }
+        p->cap_nodes = M;
+    }
+    const int64_t nCTA = (M + 4095) / 4096;
+    ST_TRY(ensure(p, (void**)&p->d_hist, &p->cap_hist, std::max<int64_t>(1, nCTA) * 256 * 4));
+    p->M = M;
+    const void* dk = nullptr;
+    ST_TRY(stage_in(p, k, M * p->D * (int64_t)p->esz(), where, &p->d_stage_k, &p->cap_stage_k, &dk));
+    ST_TRY(nfftb_sort_nodes(p, dk));
+    p->h_tile_start.resize((size_t)p->ntiles + 1);
+    CUDA_TRY(p, cudaMemcpyAsync(p->h_tile_start.data(), p->d_tile_start, sizeof(int32_t) * (size_t)(p->ntiles + 1),
+                                cudaMemcpyDeviceToHost, p->stream));
+    if (p->timing) cudaEventRecord(p->ev[1], p->stream);
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    if (p->timing) { float ms = 0; cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->t[0] = ms * 1e-3; }
+    p->have_nodes = true;
+    return NFFTB200_OK;
+}
+
+int nfftb200_get_permutation(nfftb200_plan* p, int64_t* perm, int64_t* tile_start)
+{
+    if (!p || !p->have_nodes) return nfftb_fail(p, NFFTB200_NO_NODES, "plan has no nodes");
+    DeviceGuard guard(p->device);
+    if (perm && p->M > 0) {
+        std::vector<int32_t> h((size_t)p->M);
+        CUDA_TRY(p, cudaMemcpyAsync(h.data(), p->d_perm, 4 * (size_t)p->M, cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        for (int64_t i = 0; i < p->M; i++) perm[i] = h[(size_t)i];
+    }
+    if (tile_start)
+        for (int64_t i = 0; i <= p->ntiles; i++) tile_start[i] = p->h_tile_start[(size_t)i];
+    return NFFTB200_OK;
+}
+
+int nfftb200_get_info(nfftb200_plan* p, int64_t* Nt, int64_t* block_size, int64_t* num_tiles, int64_t* lut_size,
+                      double* sigma_eff, int64_t* M)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    for (int d = 0; d < p->D; d++) {
+        if (Nt) Nt[d] = p->Nt[d];
+        if (block_size) block_size[d] = p->bs[d];
+    }
+    if (num_tiles) *num_tiles = p->ntiles;
+    if (lut_size) *lut_size = p->lut_size;
+    if (sigma_eff) *sigma_eff = p->sigma;
+    if (M) *M = p->M;
+    return NFFTB200_OK;
+}
+
+int nfftb200_get_table(nfftb200_plan* p, int which, double* out, int64_t cap, int64_t* n)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    const std::vector<double>* h = which == 0 ? &p->h_hat_inv : (which == 1 ? &p->h_poly : (which == 2 ? &p->h_lin : nullptr));
+    if (!h) return nfftb_fail(p, NFFTB200_BAD_ARGUMENT, "unknown table");
+    if (n) *n = (int64_t)h->size();
+    if (out) {
+        const size_t c = std::min<size_t>(h->size(), (size_t)std::max<int64_t>(cap, 0));
+        // values as the kernels see them (rounded to T)
+        for (size_t i = 0; i < c; i++) out[i] = p->dtype == NFFTB200_F32 ? (double)(float)(*h)[i] : (*h)[i];
+    }
+    return NFFTB200_OK;
+}
+
+int nfftb200_exec_forward(nfftb200_plan* p, const void* f, void* fHat, int where)
+{
+    if (!p || !p->have_nodes) return nfftb_fail(p, NFFTB200_NO_NODES, "plan has no nodes");
+    if (!f || !fHat) return nfftb_fail(p, NFFTB200_SIZE_MISMATCH, "Data is not consistent with NFFTPlan");
+    DeviceGuard guard(p->device);
+    const int64_t csz = 2 * (int64_t)p->esz();
+    const void* df = nullptr;
+    void* dh = nullptr;
+    ST_TRY(stage_in(p, f, p->fsz * p->B * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
+    ST_TRY(stage_out_buf(p, fHat, p->M * p->B * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
+    if (p->shard_mode == NFFTB200_SHARD_NODES) {
+        ST_TRY(nfftb_comm_exec_forward(p, df, dh));
+    } else {
+        rec(p, 0);
+        ST_TRY(nfftb_deconvolve(p, df, p->d_grid, p->B));
+        rec(p, 1);
+        ST_TRY(run_fft(p, p->d_grid, -1));
+        rec(p, 2);
+        ST_TRY(nfftb_interp(p, p->d_grid, dh, p->B, 1, 0, p->ntiles));
+        rec(p, 3);
+        p->pending = 1;
+    }
+    return stage_back(p, fHat, dh, p->M * p->B * csz, where);
+}
+
+int nfftb200_exec_adjoint(nfftb200_plan* p, const void* fHat, void* f, int where)
+{
+    if (!p || !p->have_nodes) return nfftb_fail(p, NFFTB200_NO_NODES, "plan has no nodes");
+    if (!f || !fHat) return nfftb_fail(p, NFFTB200_SIZE_MISMATCH, "Data is not consistent with NFFTPlan");
+    DeviceGuard guard(p->device);
+    const int64_t csz = 2 * (int64_t)p->esz();
+    const void* dh = nullptr;
+    void* df = nullptr;
+    ST_TRY(stage_in(p, fHat, p->M * p->B * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
+    ST_TRY(stage_out_buf(p, f, p->fsz * p->B * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
+    if (p->shard_mode == NFFTB200_SHARD_NODES) {
+        ST_TRY(nfftb_comm_exec_adjoint(p, dh, df));
+    } else {
+        rec(p, 0);
+        ST_TRY(nfftb_spread(p, dh, p->d_grid, p->B, 1, 0, p->ntiles));
+        rec(p, 1);
+        ST_TRY(run_fft(p, p->d_grid, +1));
+        rec(p, 2);
+        ST_TRY(nfftb_deconvolve_transpose(p, p->d_grid, df, p->B));
+        rec(p, 3);
+        p->pending = 2;
+    }
+    return stage_back(p, f, df, p->fsz * p->B * csz, where);
+}
+
+int nfftb200_convolve(nfftb200_plan* p, const void* g, void* fHat, int is_complex, int where)
+{
+    if (!p || !p->have_nodes) return nfftb_fail(p, NFFTB200_NO_NODES, "plan has no nodes");
+    if (!g || !fHat) return nfftb_fail(p, NFFTB200_SIZE_MISMATCH, "size(g) != Nt or size(fHat) != J");
+    DeviceGuard guard(p->device);
+    const int64_t csz = (is_complex ? 2 : 1) * (int64_t)p->esz();
+    const void* dg = nullptr;
+    void* dh = nullptr;
+    ST_TRY(stage_in(p, g, p->gsz * csz, where, &p->d_stage_g, &p->cap_stage_g, &dg));
+    ST_TRY(stage_out_buf(p, fHat, p->M * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
+    ST_TRY(nfftb_interp(p, dg, dh, 1, is_complex, 0, p->ntiles));
+    return stage_back(p, fHat, dh, p->M * csz, where);
+}
+
+int nfftb200_convolve_transpose(nfftb200_plan* p, const void* fHat, void* g, int is_complex, int where)
+{
+    if (!p || !p->have_nodes) return nfftb_fail(p, NFFTB200_NO_NODES, "plan has no nodes");
+    if (!g || !fHat) return nfftb_fail(p, NFFTB200_SIZE_MISMATCH, "size(g) != Nt or size(fHat) != J");
+    DeviceGuard guard(p->device);
+    const int64_t csz = (is_complex ? 2 : 1) * (int64_t)p->esz();
+    const void* dh = nullptr;
+    void* dg = nullptr;
+    ST_TRY(stage_in(p, fHat, p->M * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
+    ST_TRY(stage_out_buf(p, g, p->gsz * csz, where, &p->d_stage_g, &p->cap_stage_g, &dg));
+    ST_TRY(nfftb_spread(p, dh, dg, 1, is_complex, 0, p->ntiles));
+    return stage_back(p, g, dg, p->gsz * csz, where);
+}
+
+int nfftb200_deconvolve(nfftb200_plan* p, const void* f, void* g, int where)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    if (p->device < 0) return nfftb_fail(p, NFFTB200_CUDA_ERROR, "host-only plan (device < 0): no CPU fallback exists");
+    if (!g || !f) return nfftb_fail(p, NFFTB200_SIZE_MISMATCH, "Data is not consistent with NFFTPlan");
+    DeviceGuard guard(p->device);
+    const int64_t csz = 2 * (int64_t)p->esz();
+    const void* df = nullptr;
+    void* dg = nullptr;
+    ST_TRY(stage_in(p, f, p->fsz * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
+    ST_TRY(stage_out_buf(p, g, p->gsz * csz, where, &p->d_stage_g, &p->cap_stage_g, &dg));
+    ST_TRY(nfftb_deconvolve(p, df, dg, 1));
+    return stage_back(p, g, dg, p->gsz * csz, where);
+}
+
+int nfftb200_deconvolve_transpose(nfftb200_plan* p, const void* g, void* f, int where)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    if (p->device < 0) return nfftb_fail(p, NFFTB200_CUDA_ERROR, "host-only plan (device < 0): no CPU fallback exists");
+    if (!g || !f) return nfftb_fail(p, NFFTB200_SIZE_MISMATCH, "Data is not consistent with NFFTPlan");
+    DeviceGuard guard(p->device);
+    const int64_t csz = 2 * (int64_t)p->esz();
+    const void* dg = nullptr;
+    void* df = nullptr;
+    ST_TRY(stage_in(p, g, p->gsz * csz, where, &p->d_stage_g, &p->cap_stage_g, &dg));
+    ST_TRY(stage_out_buf(p, f, p->fsz * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
+    ST_TRY(nfftb_deconvolve_transpose(p, dg, df, 1));
+    return stage_back(p, f, df, p->fsz * csz, where);
+}
+
+int nfftb200_get_grid(nfftb200_plan* p, void** device_ptr)
+{
+    if (!p || !device_ptr) return NFFTB200_BAD_ARGUMENT;
+    *device_ptr = p->d_grid;
+    return NFFTB200_OK;
+}
+
+int nfftb200_fft(nfftb200_plan* p, int direction)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    if (p->device < 0) return nfftb_fail(p, NFFTB200_CUDA_ERROR, "host-only plan (device < 0): no CPU fallback exists");
+    DeviceGuard guard(p->device);
+    return run_fft(p, p->d_grid, direction);
+}
+
+int nfftb200_set_timing(nfftb200_plan* p, int enable)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    p->timing = enable != 0;
+    p->pending = 0;
+    return NFFTB200_OK;
+}
+
+int nfftb200_get_timing(nfftb200_plan* p, double out[7])
+{
+    if (!p || !out) return NFFTB200_BAD_ARGUMENT;
+    DeviceGuard guard(p->device);
+    if (p->timing && p->pending) {
+        CUDA_TRY(p, cudaEventSynchronize(p->ev[3]));
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, p->ev[0], p->ev[1]);
+        cudaEventElapsedTime(&b, p->ev[1], p->ev[2]);
+        cudaEventElapsedTime(&c, p->ev[2], p->ev[3]);
+        if (p->pending == 1) { p->t[3] = a * 1e-3; p->t[2] = b * 1e-3; p->t[1] = c * 1e-3; }   // deconv, fft, conv
+        else { p->t[4] = a * 1e-3; p->t[5] = b * 1e-3; p->t[6] = c * 1e-3; }                  // conv_adj, fft_adj, deconv_adj
+        p->pending = 0;
+    }
+    for (int i = 0; i < 7; i++) out[i] = p->t[i];
+    return NFFTB200_OK;
+}
+
+int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4])
+{
+    if (!p || !out) return NFFTB200_BAD_ARGUMENT;
+    DeviceGuard guard(p->device);
+    if (p->timing && (p->pending_k & 1)) {
+        CUDA_TRY(p, cudaEventSynchronize(p->evk[2]));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, p->evk[0], p->evk[1]);
+        cudaEventElapsedTime(&b, p->evk[1], p->evk[2]);
+        p->tk[2] = a * 1e-3; p->tk[0] = b * 1e-3;
+    }
+    if (p->timing && (p->pending_k & 2)) {
+        CUDA_TRY(p, cudaEventSynchronize(p->evk[4]));
+        float a = 0;
+        cudaEventElapsedTime(&a, p->evk[3], p->evk[4]);
+        p->tk[1] = a * 1e-3;
+    }
+    p->pending_k = 0;
+    for (int i = 0; i < 4; i++) out[i] = p->tk[i];
+    return NFFTB200_OK;
+}
+
+int nfftb200_set_kernel_mode(nfftb200_plan* p, int mode)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    p->kernel_mode = mode;
+    return NFFTB200_OK;
+}
+
+int nfftb200_get_launch_count(nfftb200_plan* p, int64_t* n)
+{
+    if (!p || !n) return NFFTB200_BAD_ARGUMENT;
+    *n = p->launches;
+    return NFFTB200_OK;
+}
+
+int nfftb200_set_stream(nfftb200_plan* p, void* cuda_stream)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    if (p->device < 0) return NFFTB200_OK;
+    DeviceGuard guard(p->device);
+    cudaStreamSynchronize(p->stream);
+    if (p->own_stream) { cudaStreamDestroy(p->stream); p->own_stream = false; }
+    p->stream = (cudaStream_t)cuda_stream;
+    CUFFT_TRY(p, cufftSetStream(p->fft, p->stream));
+    return NFFTB200_OK;
+}
+
+int nfftb200_sync(nfftb200_plan* p)
+{
+    if (!p) return NFFTB200_BAD_ARGUMENT;
+    if (p->device < 0) return NFFTB200_OK;
+    DeviceGuard guard(p->device);
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    return NFFTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+// sort.cu -- K1 + K2: node range check, shift, tile key, and a *stable* LSD radix
+// (counting) sort of node ids by tile key.  Output contract (bit-exact vs the reference):
+//   perm = concat over tiles l (column-major tile order) of nodesInBlock[l], ascending j
+//   inside a tile          -- /root/reference/src/precomputation.jl:487-504 (_precomputeBlocks)
+//   key  = sum_d (unsafe_trunc(Int, k'[d,j]*Nt[d]) / blockSize[d]) * stride_d on the
+//   shifted nodes k'       -- /root/reference/src/utils.jl:32-44, precomputation.jl:495
+// The sort is 8 bits per pass; every pass is stable (warp match + per-warp running counts +
+// per-CTA digit offsets from a global scan), so the composition is the stable counting sort
+// the reference performs serially.
+#include "common.cuh"
+#include "window.cuh"
+
+namespace {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 4096 keys per CTA
+
+template <typename T>
+__global__ void k_node_keys(const T* __restrict__ k, long long M, GeomDev g,
+                            uint32_t* __restrict__ keys, int* __restrict__ flag)
+{
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; j < M; j += stride) {
+        uint32_t key = 0, mul = 1;
+        bool bad = false;
+#pragma unroll
+        for (int d = 0; d < NFFTB_MAX_D; d++) {
+            if (d < g.D) {
+                T v = k[j * g.D + d];
+                if (!(fabs(v) <= (T)0.5)) bad = true;       // checkNodes (NaN fails too)
+                v = shift_node<T>(v);
+                T ks;
+                int c = node_cell<T>(v, g.Nt[d], ks);
+                c = min(max(c, 0), g.Nt[d] - 1);            // only reachable for rejected nodes
+                key += (uint32_t)(c / g.bs[d]) * mul;
+                mul *= (uint32_t)g.nb[d];
+            }
+        }
+        if (bad) atomicOr(flag, 1);
+        keys[j] = key;
+    }
+}
+
+__global__ void k_radix_hist(const uint32_t* __restrict__ keys, long long M, int shift,
+                             uint32_t* __restrict__ hist, int nCTA)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        long long idx = base + r * SORT_THREADS + threadIdx.x;
+        if (idx < M) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(long long)threadIdx.x * nCTA + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of n uint32 in place, one CTA of 1024 threads (plan-time only)
+__global__ void k_exclusive_scan(uint32_t* __restrict__ a, long long n)
+{
+    __shared__ uint32_t part[1024];
+    const int t = threadIdx.x;
+    const long long seg = (n + 1023) / 1024;
+    const long long lo = min((long long)t * seg, n), hi = min(lo + seg, n);
+    uint32_t s = 0;
+    for (long long i = lo; i < hi; i++) s += a[i];
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        uint32_t v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - s;
+    for (long long i = lo; i < hi; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_radix_scatter(const uint32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, long long M,
+                int shift, const uint32_t* __restrict__ hist, int nCTA)
+{
+    constexpr int NW = SORT_THREADS / 32;
+    __shared__ uint32_t wh[NW][256];
+    __shared__ uint32_t wbase[NW][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NW * 256; i += SORT_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+
+    uint32_t myk[SORT_ITEMS];
+    int32_t myv[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+    const long long base = (long long)blockIdx.x * SORT_TILE + (long long)warp * (32 * SORT_ITEMS);
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        const long long idx = base + r * 32 + lane;
+        const bool valid = idx < M;
+        const uint32_t key = valid ? keys_in[idx] : 0u;
+        myk[r] = key;
+        myv[r] = valid ? (vals_in ? vals_in[idx] : (int32_t)idx) : 0;
+        const uint32_t digit = valid ? ((key >> shift) & 255u) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t rk = __popc(peers & lt);
+        uint32_t pre = 0;
+        if (valid) pre = wh[warp][digit];
+        __syncwarp();
+        if (valid && rk == 0) wh[warp][digit] = pre + __popc(peers);
+        __syncwarp();
+        rank[r] = pre + rk;
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;                        // SORT_THREADS == 256 digits
+        uint32_t run = hist[(long long)d * nCTA + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < NW; w++) { wbase[w][d] = run; run += wh[w][d]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        const long long idx = base + r * 32 + lane;
+        if (idx < M) {
+            const uint32_t digit = (myk[r] >> shift) & 255u;
+            const uint32_t pos = wbase[warp][digit] + rank[r];
+            keys_out[pos] = myk[r];
+            vals_out[pos] = myv[r];
+        }
+    }
+}
+
+__global__ void k_iota(int32_t* v, long long M)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < M) v[i] = (int32_t)i;
+}
+
+// tile_start[t] = first sorted position whose key >= t  (keys sorted ascending)
+__global__ void k_tile_start(const uint32_t* __restrict__ keys, long long M, long long ntiles,
+                             int32_t* __restrict__ tile_start)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i > M) return;
+    const long long prev = (i == 0) ? -1 : (long long)keys[i - 1];
+    const long long cur = (i == M) ? ntiles : (long long)keys[i];
+    for (long long t = prev + 1; t <= cur; t++) tile_start[t] = (int32_t)i;
+}
+
+// shifted nodes in sorted order (physical reorder: removes the "expensive because of cache
+// misses" gather of /root/reference/src/precomputation.jl:537 from every exec)
+template <typename T>
+__global__ void k_gather_nodes(const T* __restrict__ k, const int32_t* __restrict__ perm,
+                               long long M, int D, T* __restrict__ xs)
+{
+    long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= M * D) return;
+    const long long i = q / D;
+    const int d = (int)(q - i * D);
+    xs[q] = shift_node<T>(k[(long long)perm[i] * D + d]);
+}
+
+template <typename T> int sort_impl(nfftb200_plan* p, const void* d_k)
+{
+    const long long M = p->M;
+    GeomDev g = make_geom<T>(p);
+    cudaStream_t s = p->stream;
+    CUDA_TRY(p, cudaMemsetAsync(p->d_flag, 0, sizeof(int), s));
+    if (M > 0) {
+        int blocks = (int)std::min<long long>((M + 255) / 256, 148 * 16);
+        k_node_keys<T><<<blocks, 256, 0, s>>>((const T*)d_k, M, g, p->d_keys[0], p->d_flag);
+        p->launches++;
+    }
+    int flag = 0;
+    CUDA_TRY(p, cudaMemcpyAsync(&flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(p, cudaStreamSynchronize(s));
+    if (flag) return nfftb_fail(p, NFFTB200_BAD_NODE_RANGE,
+                                "Nodes k need to be within the range [-1/2, 1/2]");
+
+    int bits = 0;
+    while ((1ll << bits) < p->ntiles) bits++;
+    const int passes = (bits + 7) / 8;
+    const int nCTA = (int)((M + SORT_TILE - 1) / SORT_TILE);
+    int cur = 0;
+    if (passes == 0 || M == 0) {
+        if (M > 0) { k_iota<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(p->d_vals[0], M); p->launches++; }
+    } else {
+        for (int ps = 0; ps < passes; ps++) {
+            const int shift = 8 * ps;
+            k_radix_hist<<<nCTA, SORT_THREADS, 0, s>>>(p->d_keys[cur], M, shift, p->d_hist, nCTA);
+            k_exclusive_scan<<<1, 1024, 0, s>>>(p->d_hist, 256ll * nCTA);
+            k_radix_scatter<<<nCTA, SORT_THREADS, 0, s>>>(
+                p->d_keys[cur], ps == 0 ? nullptr : p->d_vals[cur], p->d_keys[cur ^ 1],
+                p->d_vals[cur ^ 1], M, shift, p->d_hist, nCTA);
+            p->launches += 3;
+            cur ^= 1;
+        }
+    }
+    p->d_perm = p->d_vals[cur];
+    k_tile_start<<<(unsigned)((M + 1 + 255) / 256), 256, 0, s>>>(p->d_keys[cur], M, p->ntiles,
+                                                                 p->d_tile_start);
+    p->launches++;
+    if (M > 0) {
+        const long long n = M * p->D;
+        k_gather_nodes<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const T*)d_k, p->d_perm, M,
+                                                                    p->D, (T*)p->d_xs);
+        p->launches++;
+    }
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
+}  // namespace
+
+int nfftb_sort_nodes(nfftb200_plan* p, const void* d_k)
+{
+    return p->dtype == NFFTB200_F32 ? sort_impl<float>(p, d_k) : sort_impl<double>(p, d_k);
+}

@@ -1,0 +1,629 @@
+"""
+Host-side mirror of the AbstractNFFTs plan API for the B200 backend.
+
+The reference's host language is Julia, which is not installed in this image; the Julia glue that a
+maintainer would load is `nfft.jl_b200/julia/B200NFFT.jl` (same C ABI).  This module is the executable
+twin: same names, argument meaning and error behaviour as
+    plan_nfft / nodes! / mul! / adjoint(p) * x / size_in / size_out / convolve! / convolve_transpose! /
+    deconvolve! / deconvolve_transpose! / PrecomputeFlags / TimingStats
+(/root/reference/AbstractNFFTs/src/interface.jl:170-243, derived.jl:7-36, misc.jl:13-81,
+ /root/reference/src/implementation.jl:73-193), so that the parity tests read like the reference's tests.
+
+Array conventions (identical memory to Julia):
+  nodes  k     shape (D, M)      -- k[:, j] is node j          (Julia Matrix D x M)
+  image  f     shape N (+ (B,))  -- f[i1, i2, ...] with i1 fastest in memory (Fortran order)
+  output fHat  shape (M,) (+ (B,))
+numpy arrays are treated as HOST buffers (copied through the library's staging buffers), torch CUDA
+tensors as DEVICE buffers (zero copy; they must have the Fortran-order strides `empty_image()` gives).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import enum
+import time
+
+import numpy as np
+
+from . import _lib
+
+try:  # torch is plumbing only (device memory, streams)
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class ArgumentError(ValueError):
+    """Julia's ArgumentError"""
+
+
+class DimensionMismatch(ValueError):
+    """Julia's DimensionMismatch"""
+
+
+class PrecomputeFlags(enum.IntEnum):
+    """AbstractNFFTs/src/misc.jl:13-18"""
+    FULL = 1
+    TENSOR = 2
+    LINEAR = 3
+    POLYNOMIAL = 4
+
+
+FULL, TENSOR, LINEAR, POLYNOMIAL = (PrecomputeFlags.FULL, PrecomputeFlags.TENSOR,
+                                    PrecomputeFlags.LINEAR, PrecomputeFlags.POLYNOMIAL)
+
+
+@dataclasses.dataclass
+class TimingStats:
+    """AbstractNFFTs/src/misc.jl:22-42 (seconds)"""
+    pre: float = 0.0
+    conv: float = 0.0
+    fft: float = 0.0
+    deconv: float = 0.0
+    conv_adjoint: float = 0.0
+    fft_adjoint: float = 0.0
+    deconv_adjoint: float = 0.0
+
+
+@dataclasses.dataclass
+class NFFTParams:
+    """src/implementation.jl:3-14"""
+    m: int
+    σ: float
+    reltol: float
+    window: str
+    LUTSize: int
+    precompute: PrecomputeFlags
+    sortNodes: bool
+    storeDeconvolutionIdx: bool
+    blocking: bool
+    blockSize: tuple
+
+    @property
+    def sigma(self):
+        return self.σ
+
+
+_STATUS_EXC = {1: ArgumentError, 2: ArgumentError, 3: DimensionMismatch, 4: NotImplementedError,
+               5: RuntimeError, 6: RuntimeError, 7: MemoryError, 8: ArgumentError, 9: RuntimeError}
+
+HOST, DEVICE = 0, 1
+
+
+def _check(handle, status):
+    if status != 0:
+        L = _lib.lib()
+        msg = L.nfftb200_last_error(handle)
+        msg = msg.decode() if msg else ""
+        raise _STATUS_EXC.get(status, RuntimeError)(
+            f"{L.nfftb200_status_string(status).decode()}: {msg}")
+
+
+def accuracyParams(m=None, σ=None, reltol=None):
+    """AbstractNFFTs/src/misc.jl:66-81"""
+    mo, so, ro = C.c_int(), C.c_double(), C.c_double()
+    _lib.lib().nfftb200_accuracy_params(int(m or 0), float(σ or 0.0), float(reltol or 0.0),
+                                        C.byref(mo), C.byref(so), C.byref(ro))
+    return mo.value, so.value, ro.value
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _fortran_strides(shape):
+    s, acc = [], 1
+    for n in shape:
+        s.append(acc)
+        acc *= n
+    return tuple(s)
+
+
+class _Buf:
+    """pointer + location of a caller array; keeps converted copies alive"""
+
+    def __init__(self, ptr, where, keep, copied_from=None):
+        self.ptr, self.where, self.keep, self.copied_from = ptr, where, keep, copied_from
+
+
+class B200NFFTPlan:
+    """NFFTPlan{T,D,1} on one B200 (src/implementation.jl:16-43): opaque C handle + mirrored fields."""
+
+    def __init__(self, k, N, *, m=None, σ=None, sigma=None, reltol=None, window="kaiser_bessel",
+                 precompute=POLYNOMIAL, ntransforms=1, blockSize=None, dims=None, device=None,
+                 sortNodes=False, storeDeconvolutionIdx=False, blocking=True, fftflags=None,
+                 LUTSize=0, timing=None, stream="current"):
+        t0 = time.perf_counter()
+        if σ is None:
+            σ = sigma
+        if isinstance(N, (int, np.integer)):
+            N = (int(N),)
+        N = tuple(int(n) for n in N)
+        D = len(N)
+        if dims is not None and tuple(dims) != tuple(range(1, D + 1)):
+            raise NotImplementedError("GPU NFFT does not work along directions right now!")  # ext/...:35-37
+        window = str(window).lstrip(":")
+        if window != "kaiser_bessel":
+            raise NotImplementedError(f"Window {window} not yet implemented!")
+        k_is_torch = _is_torch(k)
+        kshape = tuple(k.shape)
+        if len(kshape) == 1:
+            kshape = (1, kshape[0])                                  # derived.jl:23-27
+        if kshape[0] != D:
+            raise ArgumentError(f"Nodes x have dimension {kshape[0]} != {D}")   # precomputation.jl:19-21
+        if k_is_torch:
+            T = np.float32 if k.dtype == torch.float32 else np.float64
+        else:
+            k = np.asarray(k)
+            T = np.float32 if k.dtype == np.float32 else np.float64
+        self.T = T
+        self.cT = np.complex64 if T == np.float32 else np.complex128
+        m_, σ_, reltol_ = accuracyParams(m, σ, reltol)
+        self._L = _lib.lib()
+        if device is None:
+            device = k.device.index if (k_is_torch and k.is_cuda) else (
+                torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0)
+        self.device = int(device)
+        self.N = N
+        self.D = D
+        self.dims = range(1, D + 1)
+        self.ntransforms = int(ntransforms)
+        self._h = C.c_void_p()
+        Narr = (C.c_int64 * D)(*N)
+        bs = (C.c_int64 * D)(*[int(b) for b in blockSize]) if blockSize is not None else None
+        st = self._L.nfftb200_plan_create(C.byref(self._h), D, Narr, 0 if T == np.float32 else 1, m_, σ_, 0,
+                                          int(precompute), self.ntransforms, bs, self.device)
+        _check(None, st)
+        Nt = (C.c_int64 * D)()
+        bso = (C.c_int64 * D)()
+        nt, lut, sg, M = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+        self._L.nfftb200_get_info(self._h, Nt, bso, C.byref(nt), C.byref(lut), C.byref(sg), C.byref(M))
+        self.Ñ = tuple(Nt)
+        self.num_tiles = nt.value
+        self.params = NFFTParams(m=m_, σ=sg.value, reltol=reltol_, window=window, LUTSize=lut.value,
+                                 precompute=PrecomputeFlags(int(precompute)), sortNodes=bool(sortNodes),
+                                 storeDeconvolutionIdx=bool(storeDeconvolutionIdx), blocking=bool(blocking),
+                                 blockSize=tuple(bso))
+        if stream == "current" and torch is not None and torch.cuda.is_available():
+            self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._timing_on = False
+        self.J = 0
+        self.NOut = (0,)
+        self.k = None
+        self.nodes_(k)
+        if timing is not None:
+            timing.pre = time.perf_counter() - t0                      # src/NFFT.jl:51-56
+
+    # aliases for ASCII-only callers
+    @property
+    def Nt(self):
+        return self.Ñ
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def destroy(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._L.nfftb200_destroy(h)
+            self._h = C.c_void_p()
+
+    def __repr__(self):
+        return (f"B200NFFTPlan with {self.J} sampling points for an input array of size{self.N} and an "
+                f"output array of size{self.NOut} with dims {tuple(self.dims)}")
+
+    # ---- interface.jl:170-211 -----------------------------------------------------------------
+    def size_in(self):
+        return self.N
+
+    def size_out(self):
+        return self.NOut
+
+    def adjoint(self):
+        return AdjointPlan(self)
+
+    @property
+    def H(self):
+        return AdjointPlan(self)
+
+    def set_stream(self, cuda_stream: int):
+        _check(self._h, self._L.nfftb200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        _check(self._h, self._L.nfftb200_sync(self._h))
+
+    def set_kernel_mode(self, mode: int):
+        _check(self._h, self._L.nfftb200_set_kernel_mode(self._h, int(mode)))
+
+    def kernel_times(self):
+        """device seconds of the last (spread kernel, interp kernel, grid memset); needs timing enabled"""
+        t = (C.c_double * 4)()
+        _check(self._h, self._L.nfftb200_get_kernel_times(self._h, t))
+        return {"spread": t[0], "interp": t[1], "memset": t[2]}
+
+    def enable_timing(self, on=True):
+        self._L.nfftb200_set_timing(self._h, int(on))
+        self._timing_on = bool(on)
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._L.nfftb200_get_launch_count(self._h, C.byref(n))
+        return n.value
+
+    # ---- nodes!(p, k)  src/implementation.jl:108-141 --------------------------------------------
+    def nodes_(self, k):
+        D = self.D
+        if _is_torch(k) and k.is_cuda:
+            kk = k if k.dim() == 2 else k.reshape(1, -1)
+            if kk.shape[0] != D:
+                raise ArgumentError(f"Nodes x have dimension {kk.shape[0]} != {D}")
+            want = torch.float32 if self.T == np.float32 else torch.float64
+            kt = kk.to(want).t().contiguous()                         # memory: node-major == Julia D x M
+            M = kt.shape[0]
+            st = self._L.nfftb200_set_nodes(self._h, C.c_void_p(kt.data_ptr()), M, DEVICE)
+            _check(self._h, st)
+            self.k = k
+        else:
+            ka = np.asarray(k.cpu().numpy() if _is_torch(k) else k)
+            if ka.ndim == 1:
+                ka = ka.reshape(1, -1)
+            if ka.shape[0] != D:
+                raise ArgumentError(f"Nodes x have dimension {ka.shape[0]} != {D}")
+            if self.params.sortNodes:                                   # precomputation.jl:52-54
+                order = np.lexsort(ka[::-1])
+                ka[...] = ka[:, order]
+            kf = np.asfortranarray(ka, dtype=self.T)
+            M = kf.shape[1]
+            st = self._L.nfftb200_set_nodes(self._h, kf.ctypes.data_as(C.c_void_p), M, HOST)
+            _check(self._h, st)
+            self.k = ka
+        self.J = int(M)
+        self.NOut = (self.J,)
+        return self
+
+    # ---- plan internals exposed for parity checks ----------------------------------------------
+    def permutation(self):
+        """concat_l nodesInBlock[l] (0-based) and the tile prefix sums."""
+        perm = np.empty(self.J, dtype=np.int64)
+        ts = np.empty(self.num_tiles + 1, dtype=np.int64)
+        _check(self._h, self._L.nfftb200_get_permutation(self._h, perm.ctypes.data_as(C.c_void_p),
+                                                         ts.ctypes.data_as(C.c_void_p)))
+        return perm, ts
+
+    def table(self, which):
+        n = C.c_int64()
+        self._L.nfftb200_get_table(self._h, which, None, 0, C.byref(n))
+        out = np.empty(n.value, dtype=np.float64)
+        self._L.nfftb200_get_table(self._h, which, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n))
+        return out
+
+    @property
+    def windowHatInvLUT(self):
+        t = self.table(0)
+        out, o = [], 0
+        for n in self.N:
+            out.append(t[o:o + n].astype(self.T))
+            o += n
+        return out
+
+    @property
+    def windowPolyInterp(self):
+        t = self.table(1)
+        m = self.params.m
+        return t.reshape((2 * m + 1, 2 * m), order="F").astype(self.T) if t.size else t.reshape(0, 0)
+
+    @property
+    def windowLinInterp(self):
+        return self.table(2).astype(self.T)
+
+    @property
+    def tmpVec(self):
+        """the plan's device grid as a torch tensor view (shape Ñ (+B), Fortran strides)"""
+        ptr = C.c_void_p()
+        self._L.nfftb200_get_grid(self._h, C.byref(ptr))
+        shape = self.Ñ + ((self.ntransforms,) if self.ntransforms > 1 else ())
+        return _device_view(ptr.value, shape, self.cT, self.device, self)
+
+    # ---- buffers ---------------------------------------------------------------------------------
+    def _bshape(self, base):
+        return tuple(base) + ((self.ntransforms,) if self.ntransforms > 1 else ())
+
+    def empty_image(self, device=True, batch=True, dtype=None):
+        return _empty_fortran(self._bshape(self.N) if batch else self.N, dtype or self.cT, self.device, device)
+
+    def empty_out(self, device=True, batch=True, dtype=None):
+        return _empty_fortran(self._bshape(self.NOut) if batch else self.NOut, dtype or self.cT, self.device, device)
+
+    def empty_grid(self, device=True, dtype=None):
+        return _empty_fortran(self.Ñ, dtype or self.cT, self.device, device)
+
+    def _in(self, x, shape, dtype, what):
+        """read-only argument -> _Buf"""
+        if tuple(x.shape) != tuple(shape):
+            raise DimensionMismatch(f"{what}: size {tuple(x.shape)} != {tuple(shape)}")
+        if _is_torch(x) and x.is_cuda:
+            want = _torch_dtype(dtype)
+            if x.dtype != want:
+                x = x.to(want)
+            if tuple(x.stride()) != _fortran_strides(shape) and x.numel() > 1:
+                xf = _empty_fortran(shape, dtype, self.device, True)
+                xf.copy_(x)
+                x = xf
+            return _Buf(x.data_ptr(), DEVICE, x)
+        a = np.asarray(x.cpu().numpy() if _is_torch(x) else x)
+        a = np.asfortranarray(a, dtype=dtype)
+        return _Buf(a.ctypes.data, HOST, a)
+
+    def _out(self, x, shape, dtype, what):
+        """mutated argument -> _Buf (must already have the right dtype and layout)"""
+        if tuple(x.shape) != tuple(shape):
+            raise DimensionMismatch(f"{what}: size {tuple(x.shape)} != {tuple(shape)}")
+        if _is_torch(x) and x.is_cuda:
+            if x.dtype != _torch_dtype(dtype) or (tuple(x.stride()) != _fortran_strides(shape) and x.numel() > 1):
+                raise ArgumentError(f"{what}: output tensor must be {dtype} with Fortran-order strides "
+                                    "(use plan.empty_image()/empty_out()/empty_grid())")
+            return _Buf(x.data_ptr(), DEVICE, x)
+        if not isinstance(x, np.ndarray):
+            raise ArgumentError(f"{what}: output must be a numpy array or a CUDA tensor")
+        if x.dtype == dtype and (x.flags.f_contiguous or x.ndim <= 1 and x.flags.c_contiguous) and x.flags.writeable:
+            return _Buf(x.ctypes.data, HOST, x)
+        tmp = np.empty(shape, dtype=dtype, order="F")                  # converted on the way back
+        return _Buf(tmp.ctypes.data, HOST, tmp, copied_from=x)
+
+    @staticmethod
+    def _finish(buf):
+        if buf.copied_from is not None:
+            buf.copied_from[...] = buf.keep
+
+    def _timing(self, timing):
+        on = timing is not None or self._timing_on
+        if on != self._timing_on:
+            self._L.nfftb200_set_timing(self._h, int(on))
+            self._timing_on = on
+
+    def _fill_timing(self, timing):
+        if timing is None:
+            return
+        t = (C.c_double * 7)()
+        self._L.nfftb200_get_timing(self._h, t)
+        pre = timing.pre
+        (timing.pre, timing.conv, timing.fft, timing.deconv, timing.conv_adjoint, timing.fft_adjoint,
+         timing.deconv_adjoint) = list(t)
+        timing.pre = pre or timing.pre
+
+    # ---- mul!  src/implementation.jl:155-193 -------------------------------------------------------
+    def mul_forward(self, fHat, f, timing=None, verbose=False):
+        # consistencyCheck, src/utils.jl:98-105
+        if tuple(f.shape) != self._bshape(self.N) or tuple(fHat.shape) != self._bshape(self.NOut):
+            raise DimensionMismatch("Data is not consistent with NFFTPlan")
+        self._timing(timing)
+        bi = self._in(f, self._bshape(self.N), self.cT, "f")
+        bo = self._out(fHat, self._bshape(self.NOut), self.cT, "fHat")
+        where = DEVICE if (bi.where == DEVICE and bo.where == DEVICE) else HOST
+        bi, bo = self._same_side(bi, bo, where)
+        _check(self._h, self._L.nfftb200_exec_forward(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr), where))
+        self._finish(bo)
+        self._fill_timing(timing)
+        if verbose and timing is not None:
+            print(f"Timing: deconv={timing.deconv} fft={timing.fft} conv={timing.conv}")
+        return fHat
+
+    def mul_adjoint(self, f, fHat, timing=None, verbose=False):
+        if tuple(f.shape) != self._bshape(self.N) or tuple(fHat.shape) != self._bshape(self.NOut):
+            raise DimensionMismatch("Data is not consistent with NFFTPlan")
+        self._timing(timing)
+        bi = self._in(fHat, self._bshape(self.NOut), self.cT, "fHat")
+        bo = self._out(f, self._bshape(self.N), self.cT, "f")
+        where = DEVICE if (bi.where == DEVICE and bo.where == DEVICE) else HOST
+        bi, bo = self._same_side(bi, bo, where)
+        _check(self._h, self._L.nfftb200_exec_adjoint(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr), where))
+        self._finish(bo)
+        self._fill_timing(timing)
+        if verbose and timing is not None:
+            print(f"Timing: conv={timing.conv_adjoint} fft={timing.fft_adjoint} deconv={timing.deconv_adjoint}")
+        return f
+
+    @staticmethod
+    def _same_side(bi, bo, where):
+        if bi.where != bo.where:
+            raise ArgumentError("input and output must both be host (numpy) or both device (CUDA tensor) arrays")
+        return bi, bo
+
+    # allocating versions, derived.jl:174-208
+    def __mul__(self, f):
+        dev = _is_torch(f) and f.is_cuda
+        out = self.empty_out(device=dev, batch=True)
+        return self.mul_forward(out, f)
+
+    __matmul__ = __mul__
+
+    # ---- optional operators, interface.jl:217-243 ------------------------------------------------
+    def _real_or_complex(self, x):
+        if _is_torch(x):
+            return x.is_complex()
+        return np.iscomplexobj(x)
+
+    def convolve_(self, g, fHat):
+        """convolve!(p, g, fHat) -> fHat  (src/convolution.jl:20-53)"""
+        if tuple(g.shape) != self.Ñ:
+            raise DimensionMismatch(f"size(g)={tuple(g.shape)} ≠ Ñ = {self.Ñ}")
+        if tuple(fHat.shape) != (self.J,):
+            raise DimensionMismatch(f"size(fHat)={tuple(fHat.shape)} ≠ J = {self.J}")
+        cin, cout = self._real_or_complex(g), self._real_or_complex(fHat)
+        if cin and not cout:
+            raise ArgumentError("Complex input g requires Complex output fHat")
+        cplx = cout
+        dt = self.cT if cplx else self.T
+        bi = self._in(g if (cin or not cplx) else _to_complex(g), self.Ñ, dt, "g")
+        bo = self._out(fHat, (self.J,), dt, "fHat")
+        self._same_side(bi, bo, None)
+        _check(self._h, self._L.nfftb200_convolve(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr), int(cplx), bi.where))
+        self._finish(bo)
+        return fHat
+
+    def convolve_transpose_(self, fHat, g):
+        """convolve_transpose!(p, fHat, g) -> g  (src/convolution.jl:115-149)"""
+        if tuple(g.shape) != self.Ñ:
+            raise DimensionMismatch(f"size(g)={tuple(g.shape)} ≠ Ñ = {self.Ñ}")
+        if tuple(fHat.shape) != (self.J,):
+            raise DimensionMismatch(f"size(fHat)={tuple(fHat.shape)} ≠ J = {self.J}")
+        cin, cout = self._real_or_complex(fHat), self._real_or_complex(g)
+        if cin and not cout:
+            raise ArgumentError("Complex input fHat requires Complex output g")
+        cplx = cout
+        dt = self.cT if cplx else self.T
+        bi = self._in(fHat if (cin or not cplx) else _to_complex(fHat), (self.J,), dt, "fHat")
+        bo = self._out(g, self.Ñ, dt, "g")
+        self._same_side(bi, bo, None)
+        _check(self._h, self._L.nfftb200_convolve_transpose(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr),
+                                                            int(cplx), bi.where))
+        self._finish(bo)
+        return g
+
+    def deconvolve_(self, f, g):
+        bi = self._in(f, self.N, self.cT, "f")
+        bo = self._out(g, self.Ñ, self.cT, "g")
+        self._same_side(bi, bo, None)
+        _check(self._h, self._L.nfftb200_deconvolve(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr), bi.where))
+        self._finish(bo)
+        return g
+
+    def deconvolve_transpose_(self, g, f):
+        bi = self._in(g, self.Ñ, self.cT, "g")
+        bo = self._out(f, self.N, self.cT, "f")
+        self._same_side(bi, bo, None)
+        _check(self._h, self._L.nfftb200_deconvolve_transpose(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr), bi.where))
+        self._finish(bo)
+        return f
+
+    def fft_(self, direction):
+        _check(self._h, self._L.nfftb200_fft(self._h, int(direction)))
+
+    # ---- multi-GPU -----------------------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int, mode: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(self._h, self._L.nfftb200_comm_init(self._h, buf, rank, nranks, mode))
+
+
+class AdjointPlan:
+    """Adjoint{Complex{T}, <:Plan} (AbstractNFFTs/src/interface.jl:118-119)"""
+
+    def __init__(self, parent):
+        self.parent = parent
+
+    def size_in(self):
+        return self.parent.size_out()
+
+    def size_out(self):
+        return self.parent.size_in()
+
+    def adjoint(self):
+        return self.parent
+
+    def __mul__(self, fHat):
+        p = self.parent
+        dev = _is_torch(fHat) and fHat.is_cuda
+        out = p.empty_image(device=dev, batch=True)
+        return p.mul_adjoint(out, fHat)
+
+    __matmul__ = __mul__
+
+    def __repr__(self):
+        return "Adjoint of " + repr(self.parent)
+
+
+# ---- free functions with the reference's names -----------------------------------------------------
+def plan_nfft(k, N, **kw):
+    """plan_nfft(k, N; m, σ, reltol, window, precompute, blockSize, ntransforms, timing, ...)
+    (AbstractNFFTs/src/derived.jl:7-36, src/NFFT.jl:49-58)"""
+    return B200NFFTPlan(k, N, **kw)
+
+
+def nodes_(p, k):
+    return p.nodes_(k)
+
+
+def size_in(p):
+    return p.size_in()
+
+
+def size_out(p):
+    return p.size_out()
+
+
+def adjoint(p):
+    return p.adjoint()
+
+
+def mul_(out, p, x, timing=None, verbose=False):
+    """mul!(fHat, p, f) / mul!(f, adjoint(p), fHat)"""
+    if isinstance(p, AdjointPlan):
+        return p.parent.mul_adjoint(out, x, timing=timing, verbose=verbose)
+    return p.mul_forward(out, x, timing=timing, verbose=verbose)
+
+
+def convolve_(p, g, fHat):
+    return p.convolve_(g, fHat)
+
+
+def convolve_transpose_(p, fHat, g):
+    return p.convolve_transpose_(fHat, g)
+
+
+def deconvolve_(p, f, g):
+    return p.deconvolve_(f, g)
+
+
+def deconvolve_transpose_(p, g, f):
+    return p.deconvolve_transpose_(g, f)
+
+
+def nfft(k, f, **kw):
+    """derived.jl:140-145"""
+    p = plan_nfft(k, tuple(f.shape), **kw)
+    return p * f
+
+
+def nfft_adjoint(k, N, fHat, **kw):
+    """derived.jl:147-153"""
+    p = plan_nfft(k, N, **kw)
+    return p.adjoint() * fHat
+
+
+# ---- helpers ----------------------------------------------------------------------------------------
+def _torch_dtype(dt):
+    return {np.float32: torch.float32, np.float64: torch.float64, np.complex64: torch.complex64,
+            np.complex128: torch.complex128}[np.dtype(dt).type]
+
+
+def _to_complex(x):
+    if _is_torch(x):
+        return x.to(torch.complex64 if x.dtype == torch.float32 else torch.complex128)
+    return np.asarray(x).astype(np.complex64 if np.asarray(x).dtype == np.float32 else np.complex128)
+
+
+def _empty_fortran(shape, dtype, device, on_device):
+    shape = tuple(int(s) for s in shape)
+    if on_device:
+        t = torch.empty(shape[::-1], dtype=_torch_dtype(dtype), device=f"cuda:{device}")
+        return t.permute(*range(len(shape) - 1, -1, -1)) if len(shape) > 1 else t
+    return np.empty(shape, dtype=dtype, order="F")
+
+
+class _CudaArrayHolder:
+    def __init__(self, ptr, shape, dtype, owner):
+        typestr = np.dtype(dtype).str
+        n = int(np.prod(shape))
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self.owner = owner
+
+
+def _device_view(ptr, shape, dtype, device, owner):
+    holder = _CudaArrayHolder(ptr, shape, dtype, owner)
+    flat = torch.as_tensor(holder, device=f"cuda:{device}")
+    shape = tuple(int(s) for s in shape)
+    return flat.view(shape[::-1]).permute(*range(len(shape) - 1, -1, -1)) if len(shape) > 1 else flat
