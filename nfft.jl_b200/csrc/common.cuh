@@ -192,4 +192,5 @@ int nfftb_spread(nfftb200_plan* p, const void* d_fhat, void* d_g, int B, int is_
                  int64_t t_lo, int64_t t_hi);                                   // spread.cu
 int nfftb_interp(nfftb200_plan* p, const void* d_g, void* d_fhat, int B, int is_complex,
                  int64_t t_lo, int64_t t_hi);                                   // interp.cu
-int nfftb_build_tables(nfftb200_plan* p);                                       // tables.cpp
+int nfftb_build_tables(nfftb200_plan* p);
+size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs);                // spread.cu                                       // tables.cpp

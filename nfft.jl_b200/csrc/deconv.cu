@@ -24,38 +24,47 @@ __device__ __forceinline__ int grid_index(int i, int N, int Nt)
     return n < 0 ? n + Nt : n;
 }
 
+// One thread writes one 16-byte unit of the grid (two Float32 cells or one Float64 cell); row
+// quantities (u1,u2 -> i1,i2, LUT factors) are block-uniform.  blockIdx.z = u2 + Nt2 * batch.
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_deconv_fwd(const typename Cplx<T>::type* __restrict__ f, typename Cplx<T>::type* __restrict__ g,
-             GeomDev geo, const T* __restrict__ lut, int B)
+             GeomDev geo, const T* __restrict__ lut)
 {
     using C = typename Cplx<T>::type;
-    const int u0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int u1 = blockIdx.y * blockDim.y + threadIdx.y;
-    const int u2 = blockIdx.z;
-    if (u0 >= geo.Nt[0] || u1 >= geo.Nt[1]) return;
-    const int i0 = img_index(u0, geo.N[0], geo.Nt[0]);
+    constexpr int VPC = 16 / (int)sizeof(C);
+    const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * VPC;
+    const int u1 = blockIdx.y;
+    const int u2 = blockIdx.z % geo.Nt[2];
+    const int b = blockIdx.z / geo.Nt[2];
+    if (u0 >= geo.Nt[0]) return;
     const int i1 = geo.D > 1 ? img_index(u1, geo.N[1], geo.Nt[1]) : 0;
     const int i2 = geo.D > 2 ? img_index(u2, geo.N[2], geo.Nt[2]) : 0;
-    const long long gq = ((long long)u2 * geo.Nt[1] + u1) * geo.Nt[0] + u0;
-    const bool in = (i0 >= 0) && (i1 >= 0) && (i2 >= 0);
-    T s0 = 0, s1 = 1, s2 = 1;
-    long long fq = 0;
-    if (in) {
-        s0 = lut[i0];
-        if (geo.D > 1) s1 = lut[geo.N[0] + i1];
-        if (geo.D > 2) s2 = lut[geo.N[0] + geo.N[1] + i2];
-        fq = ((long long)i2 * geo.N[1] + i1) * geo.N[0] + i0;
-    }
-    for (int b = 0; b < B; b++) {
-        C v = make_c<T>(0, 0);
-        if (in) {
-            v = f[b * geo.fsz + fq];
-            v.x *= s0; v.y *= s0;
-            if (geo.D > 1) { v.x *= s1; v.y *= s1; }
-            if (geo.D > 2) { v.x *= s2; v.y *= s2; }
+    C* dst = g + (size_t)b * geo.gsz + ((size_t)u2 * geo.Nt[1] + u1) * geo.Nt[0] + u0;
+    C out[VPC];
+#pragma unroll
+    for (int k = 0; k < VPC; k++) out[k] = make_c<T>(0, 0);
+    if (i1 >= 0 && i2 >= 0) {
+        const T s1 = geo.D > 1 ? lut[geo.N[0] + i1] : (T)1;
+        const T s2 = geo.D > 2 ? lut[geo.N[0] + geo.N[1] + i2] : (T)1;
+        const C* src = f + (size_t)b * geo.fsz + ((size_t)i2 * geo.N[1] + i1) * geo.N[0];
+#pragma unroll
+        for (int k = 0; k < VPC; k++) {
+            const int i0 = img_index(u0 + k, geo.N[0], geo.Nt[0]);
+            if (i0 >= 0) {
+                C v = src[i0];
+                const T s0 = lut[i0];
+                v.x *= s0; v.y *= s0;
+                if (geo.D > 1) { v.x *= s1; v.y *= s1; }
+                if (geo.D > 2) { v.x *= s2; v.y *= s2; }
+                out[k] = v;
+            }
         }
-        g[b * geo.gsz + gq] = v;
+    }
+    if (VPC == 2) {
+        *reinterpret_cast<float4*>(dst) = make_float4((float)out[0].x, (float)out[0].y, (float)out[VPC - 1].x, (float)out[VPC - 1].y);
+    } else {
+        dst[0] = out[0];
     }
 }
 
@@ -102,9 +111,12 @@ template <typename T> int deconv_impl(nfftb200_plan* p, const void* src, void* d
     GeomDev geo = make_geom<T>(p);
     dim3 grid, block;
     if (!adj) {
-        launch_dims(geo.Nt[0], geo.Nt[1], geo.Nt[2], grid, block);
-        k_deconv_fwd<T><<<grid, block, 0, p->stream>>>((const C*)src, (C*)dst, geo,
-                                                       (const T*)p->d_hat_inv, B);
+        constexpr int VPC = 16 / (int)sizeof(C);
+        const int units = (geo.Nt[0] + VPC - 1) / VPC;                      // Nt[0] is even
+        int bx = 32;
+        while (bx < 256 && bx < units) bx <<= 1;
+        grid = dim3((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);
+        k_deconv_fwd<T><<<grid, bx, 0, p->stream>>>((const C*)src, (C*)dst, geo, (const T*)p->d_hat_inv);
     } else {
         launch_dims(geo.N[0], geo.N[1], geo.N[2], grid, block);
         k_deconv_adj<T><<<grid, block, 0, p->stream>>>((const C*)src, (C*)dst, geo,

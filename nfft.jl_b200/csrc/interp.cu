@@ -10,6 +10,7 @@
 //    because a plane footprint spans 2m consecutive words per row), warp-shuffle reduction at the end.
 #include "common.cuh"
 #include "window.cuh"
+#include "tile3d.cuh"
 
 namespace {
 
@@ -17,6 +18,17 @@ __device__ __forceinline__ int wrap(int v, int n)
 {
     v %= n;
     return v < 0 ? v + n : v;
+}
+
+// asynchronous global -> shared copy of one complex cell (LDGSTS; no register staging, every row of the
+// tile is in flight at once)
+__device__ __forceinline__ void cp_async_cell(float2* dst, const float2* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_cell(double2* dst, const double2* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
 template <typename T> __device__ __forceinline__ T warp_sum(T v)
@@ -78,28 +90,44 @@ k_interp_generic(const void* __restrict__ g_, void* __restrict__ fhat_, const T*
 
 constexpr int TI_WARPS = 8;
 constexpr int TI_THREADS = TI_WARPS * 32;
-constexpr int TI_CHUNK = 128;
+
+template <typename T, int MT> struct InterpLayout {
+    using RG = RowGeom<T, MT>;
+    static constexpr int L = 2 * MT;
+    static constexpr int RW = ((RG::NWX + 2 * L) + 3) & ~3;         // record: wx(shifted) | wy | wz
+    int PX, PY, PZ, PN;
+    __host__ __device__ InterpLayout(const int* bs)
+    {
+        PX = bs[0] + L; PY = bs[1] + L; PZ = bs[2] + L;
+        PN = (PX * PY * PZ + 2 * RG::VPC + 1) & ~1;
+    }
+    __host__ __device__ size_t bytes() const
+    {
+        return sizeof(typename Cplx<T>::type) * (size_t)(PN + TI_WARPS * 32) + sizeof(T) * TI_WARPS * 32 * RW +
+               sizeof(int) * TI_WARPS * 64;
+    }
+};
 
 template <typename T, int MT>
 __global__ void __launch_bounds__(TI_THREADS)
-k_interp_tile3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::type* __restrict__ fhat,
-                const T* __restrict__ xs, const int32_t* __restrict__ perm,
-                const int32_t* __restrict__ tile_start, int tile_lo, long long M, GeomDev geo,
-                WinDev<T> win)
+k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::type* __restrict__ fhat,
+               const T* __restrict__ xs, const int32_t* __restrict__ perm,
+               const int32_t* __restrict__ tile_start, int tile_lo, long long M, GeomDev geo,
+               WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp)
 {
     using C = typename Cplx<T>::type;
-    constexpr int L = 2 * MT;
-    constexpr int NIT = (L * L + 31) / 32;
+    using RG = RowGeom<T, MT>;
+    using IL = InterpLayout<T, MT>;
+    constexpr int L = 2 * MT, VPC = RG::VPC, NV = RG::NV, NWX = RG::NWX, RW = IL::RW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
-    const int ncell = PX * PY * PZ;
-    C* tile = reinterpret_cast<C*>(smem_raw);
-    T* s_w = reinterpret_cast<T*>(tile + ncell);                       // [2][CHUNK][3L]
-    int* s_base = reinterpret_cast<int*>(s_w + 2 * TI_CHUNK * 3 * L);  // [2][CHUNK]
-    int* s_j = s_base + 2 * TI_CHUNK;                                  // [2][CHUNK]
+    const IL lay(geo.bs);
+    const int PX = lay.PX, PY = lay.PY, PZ = lay.PZ;
+    C* tile = reinterpret_cast<C*>(smem_raw);                                   // [PN]
+    C* res = tile + lay.PN;                                                     // [8][32]
+    T* rec_w = reinterpret_cast<T*>(res + TI_WARPS * 32);                       // [8][32][RW]
+    int* rec_i = reinterpret_cast<int*>(rec_w + TI_WARPS * 32 * RW);            // [8][32][2]
 
     const int tile_id = tile_lo + blockIdx.x;
-    const int b = blockIdx.y;
     const int n_lo = tile_start[tile_id], n_hi = tile_start[tile_id + 1];
     if (n_hi == n_lo) return;
     const int tx = tile_id % geo.nb[0];
@@ -107,82 +135,139 @@ k_interp_tile3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::
     const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
     const int x0 = tx * geo.bs[0] - MT, y0 = ty * geo.bs[1] - MT, z0 = tz * geo.bs[2] - MT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    g += (long long)b * geo.gsz;
-    fhat += (long long)b * M;
+    g += (long long)blockIdx.y * geo.gsz;
+    fhat += (long long)blockIdx.y * M;
 
-    // toBlock!: stage the padded tile, x fastest (coalesced within each row segment)
-    for (int q = threadIdx.x; q < ncell; q += TI_THREADS) {
-        const int x = q % PX, r = q / PX;
-        const int y = r % PY, z = r / PY;
-        const long long gi = ((long long)wrap(z0 + z, geo.Nt[2]) * geo.Nt[1] + wrap(y0 + y, geo.Nt[1])) * geo.Nt[0] +
-                             wrap(x0 + x, geo.Nt[0]);
-        tile[q] = g[gi];
+    // toBlock!: stage the padded tile; one warp per (z,y) row, lanes along x (coalesced row segments).
+    // Index math is kept lean: no integer division, 32-bit offsets, conditional periodic wrap.
+    {
+        const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
+        const unsigned inv = fastdiv_inv(PY);
+        const int gx0 = wrapc(x0 + lane, geo.Nt[0], fw);
+        for (int row = warp; row < PY * PZ; row += TI_WARPS) {
+            const int z = (int)fastdiv(row, inv), y = row - z * PY;
+            const unsigned ro = ((unsigned)wrapc(z0 + z, geo.Nt[2], fw) * geo.Nt[1] + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
+            const C* src = g + ro;
+            C* dst = tile + row * PX;
+            if (lane < PX) cp_async_cell(dst + lane, src + gx0);
+            for (int x = lane + 32; x < PX; x += 32) cp_async_cell(dst + x, src + wrapc(x0 + x, geo.Nt[0], fw));
+        }
     }
+    if (threadIdx.x < lay.PN - PX * PY * PZ) tile[PX * PY * PZ + threadIdx.x] = make_c<T>(0, 0);
 
-    int coff[NIT], xo[NIT], yo[NIT];
+    int rowoff[RG::FULL_IT > 0 ? RG::FULL_IT : 1], wyo[RG::FULL_IT > 0 ? RG::FULL_IT : 1],
+        wzo[RG::FULL_IT > 0 ? RG::FULL_IT : 1];
 #pragma unroll
-    for (int it = 0; it < NIT; it++) {
-        const int q = lane + 32 * it;
-        const int yt = q / L, xt = q - yt * L;
-        yo[it] = yt; xo[it] = xt; coff[it] = yt * PX + xt;
+    for (int it = 0; it < RG::FULL_IT; it++) {
+        const int r = lane + 32 * it, t = r / L, yt = r - t * L;
+        rowoff[it] = (t * PY + yt) * PX; wyo[it] = NWX + yt; wzo[it] = NWX + L + t;
     }
-
-    auto phase_a = [&](int buf, int c_lo, int nc) {
-        T* w = s_w + buf * TI_CHUNK * 3 * L;
-        for (int q = threadIdx.x; q < nc * 3 * L; q += TI_THREADS) {
-            const int n = q / (3 * L), r = q - n * (3 * L);
-            const int d = r / L, l = r - d * L;
-            T ks;
-            const int c = node_cell<T>(xs[(long long)(c_lo + n) * 3 + d], geo.Nt[d], ks);
-            w[q] = node_tap<T>(win, ks, c, l);
-        }
-        for (int n = threadIdx.x; n < nc; n += TI_THREADS) {
-            const long long i = c_lo + n;
-            T ks;
-            const int cx = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks);
-            const int cy = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks);
-            const int cz = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks);
-            const int ox = cx - MT + 1 - x0, oy = cy - MT + 1 - y0, oz = cz - MT + 1 - z0;
-            s_base[buf * TI_CHUNK + n] = (oz * PY + oy) * PX + ox;
-            s_j[buf * TI_CHUNK + n] = perm[i];
-        }
-    };
-
-    phase_a(0, n_lo, min(TI_CHUNK, n_hi - n_lo));
+    int rem_off = 0, rem_wy = 0, rem_wz = 0, rem_u = 0;
+    bool rem_on = false;
+    if (RG::REM > 0) {
+        const int rr = RG::SPLIT ? lane / NV : lane;
+        rem_u = RG::SPLIT ? lane - rr * NV : 0;
+        rem_on = rr < RG::REM;
+        const int r = RG::FULL_IT * 32 + (rem_on ? rr : 0), t = r / L, yt = r - t * L;
+        rem_off = (t * PY + yt) * PX + rem_u * VPC; rem_wy = NWX + yt; rem_wz = NWX + L + t;
+    }
+    T* myrec = rec_w + warp * 32 * RW;
+    int* myint = rec_i + warp * 64;
+    C* myres = res + warp * 32;
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    int buf = 0;
-    for (int c_lo = n_lo; c_lo < n_hi; c_lo += TI_CHUNK, buf ^= 1) {
-        const int nc = min(TI_CHUNK, n_hi - c_lo);
-        const int nxt = c_lo + TI_CHUNK;
-        if (nxt < n_hi) phase_a(buf ^ 1, nxt, min(TI_CHUNK, n_hi - nxt));
-        const T* w = s_w + buf * TI_CHUNK * 3 * L;
-        const int* bb = s_base + buf * TI_CHUNK;
-        const int* jj = s_j + buf * TI_CHUNK;
-        for (int n = warp; n < nc; n += TI_WARPS) {
-            const T* wn = w + n * 3 * L;
-            const C* base = tile + bb[n];
-            T sx = 0, sy = 0;
+
+    for (int rbase = n_lo + 32 * warp; rbase < n_hi; rbase += 32 * TI_WARPS) {
+        const int nn = min(32, n_hi - rbase);
+        // ---- phase A: lane-per-node weights
+        if (lane < nn) {
+            const long long i = (long long)rbase + lane;
+            T ks0, ks1, ks2;
+            const int c0 = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks0);
+            const int c1 = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks1);
+            const int c2 = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks2);
+            T w0[L], w1[L], w2[L];
+            eval_taps<T, MT>(win, pp, ks0, c0, w0);
+            eval_taps<T, MT>(win, pp, ks1, c1, w1);
+            eval_taps<T, MT>(win, pp, ks2, c2, w2);
+            const int px = c0 - MT + 1 - x0, py = c1 - MT + 1 - y0, pz = c2 - MT + 1 - z0;
+            const int s = (VPC == 2) ? (px & 1) : 0;
+            myint[2 * lane] = (pz * PY + py) * PX + (px - s);
+            myint[2 * lane + 1] = perm[i];
+            T* dst = myrec + lane * RW;
 #pragma unroll
-            for (int it = 0; it < NIT; it++) {
-                if (lane + 32 * it < L * L) {
-                    T ax = 0, ay = 0;
+            for (int k = 0; k < NWX; k++) {
+                const T lo = (k < L) ? w0[k < L ? k : 0] : (T)0;
+                const T hi = (k >= 1 && k - 1 < L) ? w0[(k >= 1 && k - 1 < L) ? k - 1 : 0] : (T)0;
+                dst[k] = s ? hi : lo;
+            }
 #pragma unroll
-                    for (int t = 0; t < L; t++) {
-                        const C v = base[t * PY * PX + coff[it]];
-                        const T wz = wn[2 * L + t];
-                        ax = tfma(wz, v.x, ax);
-                        ay = tfma(wz, v.y, ay);
-                    }
-                    const T wxy = wn[xo[it]] * wn[L + yo[it]];
-                    sx = tfma(wxy, ax, sx);
-                    sy = tfma(wxy, ay, sy);
+            for (int k = 0; k < L; k++) { dst[NWX + k] = w1[k]; dst[NWX + L + k] = w2[k]; }
+        }
+        __syncwarp();
+        // ---- phase B: gather, one node at a time, every lane owns one x-row of the footprint; the record
+        //      of node n+1 is fetched while node n is reduced (software pipelining)
+        constexpr int NIT = RG::FULL_IT > 0 ? RG::FULL_IT : 1;
+        T wx[NWX], wq[NIT], rq = 0, rwu[VPC];
+        int base;
+        auto fetch = [&](int n, T (&wx_)[NWX], T (&wq_)[NIT], T& rq_, T (&wu_)[VPC], int& base_) {
+            const T* rw = myrec + n * RW;
+            base_ = myint[2 * n];
+#pragma unroll
+            for (int k = 0; k < NWX; k++) wx_[k] = rw[k];
+#pragma unroll
+            for (int it = 0; it < RG::FULL_IT; it++) wq_[it] = rw[wyo[it]] * rw[wzo[it]];
+            if (RG::REM > 0) {
+                rq_ = rw[rem_wy] * rw[rem_wz];
+                if (RG::SPLIT) {
+#pragma unroll
+                    for (int k = 0; k < VPC; k++) wu_[k] = rw[rem_u * VPC + k];
                 }
+            }
+        };
+        fetch(0, wx, wq, rq, rwu, base);
+        for (int n = 0; n < nn; n++) {
+            const C* p0 = tile + base;
+            T wx2[NWX], wq2[NIT], rq2 = 0, rwu2[VPC];
+            int base2 = base;
+            T sx = 0, sy = 0;
+            if (RG::FULL_IT == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, wq2, rq2, rwu2, base2);
+#pragma unroll
+            for (int it = 0; it < RG::FULL_IT; it++) {
+                const C* p = p0 + rowoff[it];
+                Unit<T> U[NV];
+#pragma unroll
+                for (int u = 0; u < NV; u++) U[u].load(p + u * VPC);
+                if (it == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, wq2, rq2, rwu2, base2);
+                T a = 0, b = 0;
+#pragma unroll
+                for (int u = 0; u < NV; u++) U[u].dot(&wx[u * VPC], a, b);
+                sx = tfma(wq[it], a, sx); sy = tfma(wq[it], b, sy);
+            }
+            if (RG::REM > 0 && rem_on) {
+                const C* p = p0 + rem_off;
+                T a = 0, b = 0;
+                if (RG::SPLIT) { Unit<T> U; U.load(p); U.dot(rwu, a, b); }
+                else {
+#pragma unroll
+                    for (int u = 0; u < NV; u++) { Unit<T> U; U.load(p + u * VPC); U.dot(&wx[u * VPC], a, b); }
+                }
+                sx = tfma(rq, a, sx); sy = tfma(rq, b, sy);
             }
             sx = warp_sum<T>(sx);
             sy = warp_sum<T>(sy);
-            if (lane == 0) fhat[jj[n]] = make_c<T>(sx, sy);
+            if (lane == 0) myres[n] = make_c<T>(sx, sy);
+#pragma unroll
+            for (int k = 0; k < NWX; k++) wx[k] = wx2[k];
+#pragma unroll
+            for (int it = 0; it < NIT; it++) wq[it] = wq2[it];
+            rq = rq2; base = base2;
+#pragma unroll
+            for (int k = 0; k < VPC; k++) rwu[k] = rwu2[k];
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane < nn) fhat[myint[2 * lane + 1]] = myres[lane];
+        __syncwarp();
     }
 }
 
@@ -190,16 +275,16 @@ template <typename T, int MT>
 int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi)
 {
     using C = typename Cplx<T>::type;
-    const int L = 2 * MT;
-    const int PX = (int)p->bs[0] + L, PY = (int)p->bs[1] + L, PZ = (int)p->bs[2] + L;
-    const size_t smem = sizeof(C) * (size_t)PX * PY * PZ +
-                        2 * (sizeof(T) * TI_CHUNK * 3 * L + 2 * sizeof(int) * TI_CHUNK);
+    GeomDev geo = make_geom<T>(p);
+    InterpLayout<T, MT> lay(geo.bs);
+    const size_t smem = lay.bytes();
     if (smem > 227 * 1024) return -1;
-    auto kern = k_interp_tile3d<T, MT>;
+    auto kern = k_interp_row3d<T, MT>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(t_hi - t_lo, B);
     kern<<<grid, TI_THREADS, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm,
-                                               p->d_tile_start, t_lo, p->M, make_geom<T>(p), make_win<T>(p));
+                                               p->d_tile_start, t_lo, p->M, geo, make_win<T>(p),
+                                               make_poly_param<T, MT>(p));
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;

@@ -57,8 +57,8 @@ int upload_table(nfftb200_plan* p, const std::vector<double>& h, void** d)
     return NFFTB200_OK;
 }
 
-// reference defaults (src/precomputation.jl:59-77), shrunk in 3-D only when the padded tile would
-// not fit the 227 KB of shared memory the tiled kernels use
+// reference defaults (src/precomputation.jl:59-77: 1-D 1024, 2-D 64x64, 3-D 16^3); in 3-D the tile is
+// shrunk only when the warp-private sub-tiles of the spreader would not fit 227 KB of shared memory
 void default_tiles(nfftb200_plan* p)
 {
     const int D = p->D;
@@ -67,14 +67,14 @@ void default_tiles(nfftb200_plan* p)
         p->bs[d] = std::min<int64_t>(v, p->Nt[d]);
     }
     if (D == 3) {
-        const int64_t csz = 2 * (int64_t)p->esz();
-        auto fits = [&]() {
-            int64_t c = 1;
-            for (int d = 0; d < 3; d++) c *= p->bs[d] + 2 * p->m;
-            return c * csz + 32 * 1024 <= 227 * 1024;
-        };
-        if (!fits()) p->bs[2] = std::min<int64_t>(8, p->Nt[2]);
-        if (!fits()) { p->bs[0] = std::min<int64_t>(8, p->Nt[0]); p->bs[1] = std::min<int64_t>(8, p->Nt[1]); }
+        static const int cand[][3] = {{16, 16, 16}, {16, 16, 8}, {16, 8, 8}, {8, 8, 8}, {8, 8, 4}, {8, 4, 4}, {4, 4, 4}};
+        for (auto& c : cand) {
+            int64_t bs[3];
+            for (int d = 0; d < 3; d++) bs[d] = std::min<int64_t>(c[d], p->Nt[d]);
+            const size_t need = nfftb_spread3d_smem(p->dtype, p->m, bs);
+            if (need == 0) break;                       // no tiled kernel for this m: keep the reference default
+            if (need <= 227 * 1024) { for (int d = 0; d < 3; d++) p->bs[d] = bs[d]; break; }
+        }
     }
 }
 
@@ -211,7 +211,6 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
         if (N[d] < 1) { delete p; return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "N[d] must be >= 1"); }
         p->N[d] = N[d];
         p->Nt[d] = ((int64_t)std::ceil(sig_T * (double)N[d]) / 2) * 2;
-        if (p->Nt[d] < 2 * m) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "oversampled grid smaller than the window (Nt < 2m)"); }
         if (p->Nt[d] > (1 << 30)) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "grid dimension too large"); }
     }
     if (dtype == NFFTB200_F32) {

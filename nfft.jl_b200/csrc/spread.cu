@@ -14,6 +14,7 @@
 //    The finished tile (incl. halo) is flushed with one vector RED per cell (REDG.ADD.F32x2).
 #include "common.cuh"
 #include "window.cuh"
+#include "tile3d.cuh"
 
 namespace {
 
@@ -79,131 +80,279 @@ k_spread_generic(const void* __restrict__ fhat_, void* __restrict__ g_, const T*
 }
 
 // ---------------------------------------------------------------------------------------
-// tiled 3-D spreader
+// tiled 3-D spreader: warp-private padded sub-tiles, row-per-lane accumulation
 // ---------------------------------------------------------------------------------------
-constexpr int TS_WARPS = 8;
-constexpr int TS_THREADS = TS_WARPS * 32;
-constexpr int TS_CHUNK = 128;        // nodes per record chunk
+constexpr int SS_WARPS = 8;
+constexpr int SS_THREADS = SS_WARPS * 32;
+constexpr int SS_CHUNK = 1024;       // nodes whose octant ids are cached per pass
 
-template <typename T, int MT> struct TileSmem {
+template <typename T, int MT> struct SubLayout {
+    using RG = RowGeom<T, MT>;
     static constexpr int L = 2 * MT;
-    // byte offsets inside dynamic shared memory
-    static size_t tile_bytes(int PX, int PY, int PZ) { return sizeof(typename Cplx<T>::type) * (size_t)PX * PY * PZ; }
-    static size_t rec_bytes()
+    static constexpr int RW = ((RG::NWX + L + 2 * L) + 3) & ~3;     // record: wx(shifted) | wy | wz*v
+    int SX, SY, SZ, QX, QY, QZ, QN;
+    __host__ __device__ SubLayout(const int* bs)
     {
-        return 2 * (sizeof(T) * TS_CHUNK * 3 * L + sizeof(typename Cplx<T>::type) * TS_CHUNK +
-                    2 * sizeof(int) * TS_CHUNK);
+        SX = (bs[0] + 1) / 2; SY = (bs[1] + 1) / 2; SZ = (bs[2] + 1) / 2;
+        QX = SX + L; QY = SY + L; QZ = SZ + L;
+        QN = (QX * QY * QZ + 2 * RG::VPC + 1) & ~1;                 // tail pad for the widened last row
+    }
+    __host__ __device__ size_t bytes() const
+    {
+        return sizeof(typename Cplx<T>::type) * (size_t)SS_WARPS * QN + sizeof(T) * SS_WARPS * 32 * RW +
+               sizeof(int) * SS_WARPS * 32 + sizeof(unsigned short) * SS_WARPS * 64 + SS_CHUNK;
     }
 };
 
 template <typename T, int MT>
-__global__ void __launch_bounds__(TS_THREADS)
-k_spread_tile3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>::type* __restrict__ g,
-                const T* __restrict__ xs, const int32_t* __restrict__ perm,
-                const int32_t* __restrict__ tile_start, int tile_lo, long long M, GeomDev geo,
-                WinDev<T> win)
+__global__ void __launch_bounds__(SS_THREADS, 1)
+k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>::type* __restrict__ g,
+               const T* __restrict__ xs, const int32_t* __restrict__ perm,
+               const int32_t* __restrict__ tile_start, int tile_lo, long long M, GeomDev geo,
+               WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp)
 {
     using C = typename Cplx<T>::type;
-    constexpr int L = 2 * MT;
-    constexpr int NIT = (L * L + 31) / 32;
+    using RG = RowGeom<T, MT>;
+    using SL = SubLayout<T, MT>;
+    constexpr int L = 2 * MT, VPC = RG::VPC, NV = RG::NV, NWX = RG::NWX, RW = SL::RW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
-    const int ncell = PX * PY * PZ;
-    C* tile = reinterpret_cast<C*>(smem_raw);
-    T* s_w = reinterpret_cast<T*>(tile + ncell);                       // [2][CHUNK][3L]
-    C* s_v = reinterpret_cast<C*>(s_w + 2 * TS_CHUNK * 3 * L);         // [2][CHUNK]
-    int* s_base = reinterpret_cast<int*>(s_v + 2 * TS_CHUNK);          // [2][CHUNK]
-    int* s_oz = s_base + 2 * TS_CHUNK;                                 // [2][CHUNK]
+    const SL lay(geo.bs);
+    const int QX = lay.QX, QY = lay.QY, QN = lay.QN;
+    C* sub = reinterpret_cast<C*>(smem_raw);                                    // [8][QN]
+    T* rec_w = reinterpret_cast<T*>(sub + SS_WARPS * QN);                       // [8][32][RW]
+    int* rec_b = reinterpret_cast<int*>(rec_w + SS_WARPS * 32 * RW);            // [8][32]
+    unsigned short* list = reinterpret_cast<unsigned short*>(rec_b + SS_WARPS * 32);   // [8][64]
+    unsigned char* oct = reinterpret_cast<unsigned char*>(list + SS_WARPS * 64);      // [SS_CHUNK]
 
     const int tile_id = tile_lo + blockIdx.x;
-    const int b = blockIdx.y;
     const int n_lo = tile_start[tile_id], n_hi = tile_start[tile_id + 1];
-    if (n_hi == n_lo) return;                                          // grid is pre-zeroed
+    if (n_hi == n_lo) return;                                                   // grid is pre-zeroed
     const int tx = tile_id % geo.nb[0];
     const int ty = (tile_id / geo.nb[0]) % geo.nb[1];
     const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
-    const int x0 = tx * geo.bs[0] - MT, y0 = ty * geo.bs[1] - MT, z0 = tz * geo.bs[2] - MT;
+    const int cx0 = tx * geo.bs[0], cy0 = ty * geo.bs[1], cz0 = tz * geo.bs[2];  // first core cell
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    fhat += (long long)b * M;
-    g += (long long)b * geo.gsz;
+    const int ob0 = warp & 1, ob1 = (warp >> 1) & 1, ob2 = warp >> 2;
+    fhat += (long long)blockIdx.y * M;
+    g += (long long)blockIdx.y * geo.gsz;
+    C* mysub = sub + warp * QN;
+    T* myrec = rec_w + warp * 32 * RW;
+    int* mybase = rec_b + warp * 32;
+    unsigned short* mylist = list + warp * 64;
 
-    for (int q = threadIdx.x; q < ncell; q += TS_THREADS) tile[q] = make_c<T>(0, 0);
-
-    // per-lane constant footprint offsets
-    int coff[NIT], xo[NIT], yo[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; it++) {
-        const int q = lane + 32 * it;
-        const int yt = q / L, xt = q - yt * L;
-        yo[it] = yt; xo[it] = xt; coff[it] = yt * PX + xt;
+    {   // zero all sub-tiles with 16-byte stores
+        uint4* z = reinterpret_cast<uint4*>(sub);
+        const int n16 = (int)((sizeof(C) * (size_t)SS_WARPS * QN) / 16);
+        for (int q = threadIdx.x; q < n16; q += SS_THREADS) z[q] = make_uint4(0, 0, 0, 0);
     }
 
-    auto phase_a = [&](int buf, int c_lo, int nc) {
-        T* w = s_w + buf * TS_CHUNK * 3 * L;
-        for (int q = threadIdx.x; q < nc * 3 * L; q += TS_THREADS) {
-            const int n = q / (3 * L), r = q - n * (3 * L);
-            const int d = r / L, l = r - d * L;
-            T ks;
-            const int c = node_cell<T>(xs[(long long)(c_lo + n) * 3 + d], geo.Nt[d], ks);
-            w[q] = node_tap<T>(win, ks, c, l);
+    // per-lane constant row geometry
+    int rowoff[RG::FULL_IT > 0 ? RG::FULL_IT : 1], wyo[RG::FULL_IT > 0 ? RG::FULL_IT : 1],
+        vzo[RG::FULL_IT > 0 ? RG::FULL_IT : 1];
+#pragma unroll
+    for (int it = 0; it < RG::FULL_IT; it++) {
+        const int r = lane + 32 * it, t = r / L, yt = r - t * L;
+        rowoff[it] = (t * QY + yt) * QX; wyo[it] = NWX + yt; vzo[it] = NWX + L + 2 * t;
+    }
+    int rem_off = 0, rem_wy = 0, rem_vz = 0, rem_u = 0;
+    bool rem_on = false;
+    if (RG::REM > 0) {
+        const int rr = RG::SPLIT ? lane / NV : lane;
+        rem_u = RG::SPLIT ? lane - rr * NV : 0;
+        rem_on = rr < RG::REM;
+        const int r = RG::FULL_IT * 32 + (rem_on ? rr : 0), t = r / L, yt = r - t * L;
+        rem_off = (t * QY + yt) * QX + rem_u * VPC; rem_wy = NWX + yt; rem_vz = NWX + L + 2 * t;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+
+    auto process_round = [&](int cbase, int nn) {
+        // ---- phase A: lane-per-node weights and record
+        if (lane < nn) {
+            const long long i = (long long)cbase + mylist[lane];
+            T ks0, ks1, ks2;
+            const int c0 = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks0);
+            const int c1 = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks1);
+            const int c2 = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks2);
+            T w0[L], w1[L], w2[L];
+            eval_taps<T, MT>(win, pp, ks0, c0, w0);
+            eval_taps<T, MT>(win, pp, ks1, c1, w1);
+            eval_taps<T, MT>(win, pp, ks2, c2, w2);
+            const C v = fhat[perm[i]];
+            const int px = c0 - cx0 - ob0 * lay.SX + 1, py = c1 - cy0 - ob1 * lay.SY + 1,
+                      pz = c2 - cz0 - ob2 * lay.SZ + 1;                          // first tap, padded sub-tile coords
+            const int s = (VPC == 2) ? (px & 1) : 0;
+            mybase[lane] = (pz * QY + py) * QX + (px - s);
+            T r[RW];
+#pragma unroll
+            for (int k = 0; k < NWX; k++) {
+                const T lo = (k < L) ? w0[k < L ? k : 0] : (T)0;
+                const T hi = (k >= 1 && k - 1 < L) ? w0[(k >= 1 && k - 1 < L) ? k - 1 : 0] : (T)0;
+                r[k] = s ? hi : lo;
+            }
+#pragma unroll
+            for (int k = 0; k < L; k++) r[NWX + k] = w1[k];
+#pragma unroll
+            for (int k = 0; k < L; k++) { r[NWX + L + 2 * k] = w2[k] * v.x; r[NWX + L + 2 * k + 1] = w2[k] * v.y; }
+#pragma unroll
+            for (int k = NWX + 3 * L; k < RW; k++) r[k] = (T)0;
+            T* dst = myrec + lane * RW;
+#pragma unroll
+            for (int k = 0; k < RW; k++) dst[k] = r[k];
         }
-        for (int n = threadIdx.x; n < nc; n += TS_THREADS) {
-            const long long i = c_lo + n;
-            T ks;
-            const int cx = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks);
-            const int cy = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks);
-            const int cz = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks);
-            const int ox = cx - MT + 1 - x0, oy = cy - MT + 1 - y0, oz = cz - MT + 1 - z0;
-            s_base[buf * TS_CHUNK + n] = (oz * PY + oy) * PX + ox;
-            s_oz[buf * TS_CHUNK + n] = oz;
-            s_v[buf * TS_CHUNK + n] = fhat[perm[i]];
+        __syncwarp();
+        // ---- phase B: one node at a time, every lane owns one x-row of the footprint.  The record of
+        //      node n+1 is fetched while node n is accumulated (software pipelining of the dependent loads).
+        constexpr int NIT = RG::FULL_IT > 0 ? RG::FULL_IT : 1;
+        T wx[NWX], fa[NIT], fb[NIT], ra = 0, rb = 0, rwu[VPC];
+        int base;
+        auto fetch = [&](int n, T (&wx_)[NWX], T (&fa_)[NIT], T (&fb_)[NIT], T& ra_, T& rb_, T (&wu_)[VPC], int& base_) {
+            const T* rw = myrec + n * RW;
+            base_ = mybase[n];
+#pragma unroll
+            for (int k = 0; k < NWX; k++) wx_[k] = rw[k];
+#pragma unroll
+            for (int it = 0; it < RG::FULL_IT; it++) {
+                const T wyv = rw[wyo[it]];
+                fa_[it] = wyv * rw[vzo[it]]; fb_[it] = wyv * rw[vzo[it] + 1];
+            }
+            if (RG::REM > 0) {
+                const T wyv = rw[rem_wy];
+                ra_ = wyv * rw[rem_vz]; rb_ = wyv * rw[rem_vz + 1];
+                if (RG::SPLIT) {
+#pragma unroll
+                    for (int k = 0; k < VPC; k++) wu_[k] = rw[rem_u * VPC + k];
+                }
+            }
+        };
+        fetch(0, wx, fa, fb, ra, rb, rwu, base);
+        for (int n = 0; n < nn; n++) {
+            C* p0 = mysub + base;
+            T wx2[NWX], fa2[NIT], fb2[NIT], ra2 = 0, rb2 = 0, rwu2[VPC];
+            int base2 = base;
+            if (RG::FULL_IT == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, fa2, fb2, ra2, rb2, rwu2, base2);
+#pragma unroll
+            for (int it = 0; it < RG::FULL_IT; it++) {
+                Unit<T> U[NV];
+#pragma unroll
+                for (int u = 0; u < NV; u++) U[u].load(p0 + rowoff[it] + u * VPC);
+                if (it == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, fa2, fb2, ra2, rb2, rwu2, base2);
+#pragma unroll
+                for (int u = 0; u < NV; u++) { U[u].axpy(&wx[u * VPC], fa[it], fb[it]); U[u].store(p0 + rowoff[it] + u * VPC); }
+            }
+            if (RG::REM > 0 && rem_on) {
+                if (RG::SPLIT) { Unit<T> U; U.load(p0 + rem_off); U.axpy(rwu, ra, rb); U.store(p0 + rem_off); }
+                else {
+#pragma unroll
+                    for (int u = 0; u < NV; u++) { Unit<T> U; U.load(p0 + rem_off + u * VPC); U.axpy(&wx[u * VPC], ra, rb); U.store(p0 + rem_off + u * VPC); }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NWX; k++) wx[k] = wx2[k];
+#pragma unroll
+            for (int it = 0; it < NIT; it++) { fa[it] = fa2[it]; fb[it] = fb2[it]; }
+            ra = ra2; rb = rb2; base = base2;
+#pragma unroll
+            for (int k = 0; k < VPC; k++) rwu[k] = rwu2[k];
+            __syncwarp();
         }
     };
 
-    phase_a(0, n_lo, min(TS_CHUNK, n_hi - n_lo));
+    for (int cbase = n_lo; cbase < n_hi; cbase += SS_CHUNK) {
+        const int nc = min(SS_CHUNK, n_hi - cbase);
+        __syncthreads();                                   // oct[] free, sub-tiles zeroed
+        for (int q = threadIdx.x; q < nc; q += SS_THREADS) {
+            const long long i = (long long)cbase + q;
+            T ks;
+            const int l0 = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks) - cx0;
+            const int l1 = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks) - cy0;
+            const int l2 = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks) - cz0;
+            oct[q] = (unsigned char)((l0 >= lay.SX) + 2 * (l1 >= lay.SY) + 4 * (l2 >= lay.SZ));
+        }
+        __syncthreads();
+        int cnt = 0;
+        for (int base = 0; base < nc; base += 32) {
+            const int idx = base + lane;
+            const bool mine = idx < nc && oct[idx] == warp;
+            const unsigned mask = __ballot_sync(0xffffffffu, mine);
+            if (mine) mylist[cnt + __popc(mask & lt)] = (unsigned short)idx;
+            cnt += __popc(mask);
+            __syncwarp();
+            if (cnt >= 32) {
+                process_round(cbase, 32);
+                const int rest = cnt - 32;
+                unsigned short tmp = 0;
+                if (lane < rest) tmp = mylist[32 + lane];
+                __syncwarp();
+                if (lane < rest) mylist[lane] = tmp;
+                __syncwarp();
+                cnt = rest;
+            }
+        }
+        if (cnt > 0) process_round(cbase, cnt);
+    }
     __syncthreads();
-    int buf = 0;
-    for (int c_lo = n_lo; c_lo < n_hi; c_lo += TS_CHUNK, buf ^= 1) {
-        const int nc = min(TS_CHUNK, n_hi - c_lo);
-        const int nxt = c_lo + TS_CHUNK;
-        if (nxt < n_hi) phase_a(buf ^ 1, nxt, min(TS_CHUNK, n_hi - nxt));
-        // phase B: plane-owner accumulation
-        const T* w = s_w + buf * TS_CHUNK * 3 * L;
-        const C* vv = s_v + buf * TS_CHUNK;
-        const int* bb = s_base + buf * TS_CHUNK;
-        const int* zz = s_oz + buf * TS_CHUNK;
-        for (int n = 0; n < nc; n++) {
-            const int oz = zz[n];
-            for (int t = (warp - oz) & (TS_WARPS - 1); t < L; t += TS_WARPS) {
-                const T* wn = w + n * 3 * L;
-                const T wz = wn[2 * L + t];
-                const C v = vv[n];
-                const T vzx = v.x * wz, vzy = v.y * wz;
-                C* row = tile + bb[n] + t * PY * PX;
-#pragma unroll
-                for (int it = 0; it < NIT; it++) {
-                    if (lane + 32 * it < L * L) {
-                        const T wxy = wn[xo[it]] * wn[L + yo[it]];
-                        C cur = row[coff[it]];
-                        cur.x = tfma(wxy, vzx, cur.x);
-                        cur.y = tfma(wxy, vzy, cur.y);
-                        row[coff[it]] = cur;
-                    }
-                }
+
+    // ---- hierarchical merge of the 8 warp-private sub-tiles (fixed order => deterministic), then flush.
+    //      Octant o = ox + 2*oy + 4*oz covers padded-tile cells [o_d*S_d, o_d*S_d + S_d + 2m).  The overlap of
+    //      the low octant is folded into the high one, one dimension at a time (bulk shared-memory adds):
+    //        z: planes [SZ,QZ) of (ox,oy,0)  -> planes [0,2m) of (ox,oy,1)
+    //        y: rows   [SY,QY) of (ox,0,oz)  -> rows   [0,2m) of (ox,1,oz)   (live planes only)
+    //        x: cells  [SX,QX) of (0,oy,oz)  -> cells  [0,2m) of (1,oy,oz)   (live rows only)
+    //      after which every padded-tile cell lives in exactly one sub-tile.
+    {
+        const int SX = lay.SX, SY = lay.SY, SZ = lay.SZ, QZ = lay.QZ;
+        const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
+        {   // z
+            const int blk = L * QY * QX;
+            for (int q = threadIdx.x; q < 4 * blk; q += SS_THREADS) {
+                const int col = q / blk, r = q - col * blk;
+                const C a = sub[col * QN + SZ * QY * QX + r];
+                C* d = sub + (col + 4) * QN + r;
+                C c = *d; c.x += a.x; c.y += a.y; *d = c;
             }
         }
         __syncthreads();
-    }
-
-    // flush padded tile (halo included) with one vector RED per cell
-    for (int q = threadIdx.x; q < ncell; q += TS_THREADS) {
-        const int x = q % PX, r = q / PX;
-        const int y = r % PY, z = r / PY;
-        const C v = tile[q];
-        if (v.x == (T)0 && v.y == (T)0) continue;
-        const long long gi = ((long long)wrap(z0 + z, geo.Nt[2]) * geo.Nt[1] + wrap(y0 + y, geo.Nt[1])) * geo.Nt[0] +
-                             wrap(x0 + x, geo.Nt[0]);
-        red_add_c(g + gi, v);
+        {   // y: live planes of octant oz: oz==0 -> [0,SZ), oz==1 -> [0,QZ)
+            const int blk = L * QX, npl = SZ + QZ;
+            const unsigned inv = fastdiv_inv(blk);
+            for (int q = threadIdx.x; q < 2 * npl * blk; q += SS_THREADS) {
+                const int pb = (int)fastdiv(q, inv), r = q - pb * blk;
+                const int ox_ = pb >= npl, pl = pb - ox_ * npl;
+                const int oz_ = pl >= SZ, zz = pl - oz_ * SZ;
+                const int o = ox_ + 4 * oz_;
+                const C a = sub[o * QN + (zz * QY + SY) * QX + r];
+                C* d = sub + (o + 2) * QN + zz * QY * QX + r;
+                C c = *d; c.x += a.x; c.y += a.y; *d = c;
+            }
+        }
+        __syncthreads();
+        {   // x: live rows: merged (y,z) coordinates of the padded tile
+            const unsigned invL = fastdiv_inv(L), invPY = fastdiv_inv(PY);
+            for (int q = threadIdx.x; q < PY * PZ * L; q += SS_THREADS) {
+                const int row = (int)fastdiv(q, invL), xx = q - row * L;
+                const int z = (int)fastdiv(row, invPY), y = row - z * PY;
+                const int oy_ = y >= SY, oz_ = z >= SZ;
+                const int o = 2 * oy_ + 4 * oz_;
+                const int ro = ((z - oz_ * SZ) * QY + (y - oy_ * SY)) * QX;
+                const C a = sub[o * QN + ro + SX + xx];
+                C* d = sub + (o + 1) * QN + ro + xx;
+                C c = *d; c.x += a.x; c.y += a.y; *d = c;
+            }
+        }
+        __syncthreads();
+        // flush: one vector RED (REDG.ADD.F32x2) per non-zero cell at the periodically wrapped position
+        const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
+        const unsigned inv = fastdiv_inv(PY);
+        for (int row = warp; row < PY * PZ; row += SS_WARPS) {
+            const int z = (int)fastdiv(row, inv), y = row - z * PY;
+            const int oy_ = y >= SY, oz_ = z >= SZ;
+            const C* pa = sub + (2 * oy_ + 4 * oz_) * QN + ((z - oz_ * SZ) * QY + (y - oy_ * SY)) * QX;
+            const unsigned ro = ((unsigned)wrapc(cz0 - MT + z, geo.Nt[2], fw) * geo.Nt[1] + wrapc(cy0 - MT + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
+            for (int x = lane; x < PX; x += 32) {
+                const C c = (x < SX) ? pa[x] : pa[QN + x - SX];
+                if (c.x != (T)0 || c.y != (T)0) red_add_c(g + ro + wrapc(cx0 - MT + x, geo.Nt[0], fw), c);
+            }
+        }
     }
 }
 
@@ -211,15 +360,16 @@ template <typename T, int MT>
 int launch_tile3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi)
 {
     using C = typename Cplx<T>::type;
-    const int L = 2 * MT;
-    const int PX = (int)p->bs[0] + L, PY = (int)p->bs[1] + L, PZ = (int)p->bs[2] + L;
-    const size_t smem = TileSmem<T, MT>::tile_bytes(PX, PY, PZ) + TileSmem<T, MT>::rec_bytes();
+    GeomDev geo = make_geom<T>(p);
+    SubLayout<T, MT> lay(geo.bs);
+    const size_t smem = lay.bytes();
     if (smem > 227 * 1024) return -1;
-    auto kern = k_spread_tile3d<T, MT>;
+    auto kern = k_spread_sub3d<T, MT>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(t_hi - t_lo, B);
-    kern<<<grid, TS_THREADS, smem, p->stream>>>((const C*)fhat, (C*)g, (const T*)p->d_xs, p->d_perm,
-                                               p->d_tile_start, t_lo, p->M, make_geom<T>(p), make_win<T>(p));
+    kern<<<grid, SS_THREADS, smem, p->stream>>>((const C*)fhat, (C*)g, (const T*)p->d_xs, p->d_perm,
+                                               p->d_tile_start, t_lo, p->M, geo, make_win<T>(p),
+                                               make_poly_param<T, MT>(p));
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;
@@ -266,6 +416,19 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
 }
 
 }  // namespace
+
+// shared memory the tiled 3-D spreader needs for a given tile (0 = no tiled kernel for this m)
+size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs)
+{
+    int b[3] = {(int)bs[0], (int)bs[1], (int)bs[2]};
+#define CASE_M(MM)                                                                         \
+    case MM: return dtype == NFFTB200_F32 ? SubLayout<float, MM>(b).bytes() : SubLayout<double, MM>(b).bytes();
+    switch (m) {
+        CASE_M(2) CASE_M(3) CASE_M(4) CASE_M(5) CASE_M(6)
+        default: return 0;
+    }
+#undef CASE_M
+}
 
 int nfftb_spread(nfftb200_plan* p, const void* d_fhat, void* d_g, int B, int is_complex, int64_t t_lo,
                  int64_t t_hi)

@@ -16,8 +16,8 @@ TOL = {np.float64: 1e-12, np.float32: 1e-5}
 
 
 def rel(a, b):
-    a = np.asarray(a).ravel()
-    b = np.asarray(b).ravel()
+    a = np.asarray(a).ravel().astype(np.complex128)
+    b = np.asarray(b).ravel().astype(np.complex128)
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
