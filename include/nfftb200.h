@@ -127,8 +127,9 @@ int nfftb200_get_timing(nfftb200_plan* p, double out[7]);
  * (seconds, CUDA events on the plan's stream; needs set_timing(1)): out = {spread, interp, memset, 0} */
 int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
 
-/* kernel-selection knob for benchmarking/tests: 0 = auto (tiled shared-memory kernels where
- * they apply), 1 = force the generic global-atomic kernels. */
+/* kernel-selection knob for benchmarking/tests: 0 = auto (tiled shared-memory kernels where they apply;
+ * the spreader stores per-tile sub-grids and a gather pass sums them: no global atomics), 1 = force the
+ * generic global-RED kernels, 2 = tiled kernels with the halo flushed by vector REDs. */
 int nfftb200_set_kernel_mode(nfftb200_plan* p, int mode);
 /* number of kernels + library calls this plan has launched so far */
 int nfftb200_get_launch_count(nfftb200_plan* p, int64_t* n);

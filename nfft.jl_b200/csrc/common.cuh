@@ -126,6 +126,7 @@ struct nfftb200_plan {
     int64_t node_lo = 0, node_hi = 0;  // sorted-position range owned by this rank (SHARD_NODES)
     int b_lo = 0, b_hi = 1;            // transform range owned by this rank (SHARD_BATCH)
     void* d_slab = nullptr; int64_t cap_slab = 0;
+    void* d_tilebuf = nullptr; int64_t cap_tilebuf = 0;   // per-tile padded sub-grids ("blocks") of the spreader
 
     size_t esz() const { return dtype == NFFTB200_F32 ? 4 : 8; }
 };

@@ -138,19 +138,24 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     g += (long long)blockIdx.y * geo.gsz;
     fhat += (long long)blockIdx.y * M;
 
-    // toBlock!: stage the padded tile; one warp per (z,y) row, lanes along x (coalesced row segments).
-    // Index math is kept lean: no integer division, 32-bit offsets, conditional periodic wrap.
+    // toBlock!: stage the padded tile with cp.async; one warp per (z,y) row, lanes along x (coalesced row
+    // segments).  Everything that depends only on x is hoisted; (y,z) advance incrementally; no division.
     {
         const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
-        const unsigned inv = fastdiv_inv(PY);
-        const int gx0 = wrapc(x0 + lane, geo.Nt[0], fw);
-        for (int row = warp; row < PY * PZ; row += TI_WARPS) {
-            const int z = (int)fastdiv(row, inv), y = row - z * PY;
-            const unsigned ro = ((unsigned)wrapc(z0 + z, geo.Nt[2], fw) * geo.Nt[1] + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
-            const C* src = g + ro;
-            C* dst = tile + row * PX;
-            if (lane < PX) cp_async_cell(dst + lane, src + gx0);
-            for (int x = lane + 32; x < PX; x += 32) cp_async_cell(dst + x, src + wrapc(x0 + x, geo.Nt[0], fw));
+        const int xg0 = wrapc(x0 + lane, geo.Nt[0], fw), xg1 = wrapc(x0 + lane + 32, geo.Nt[0], fw);
+        const bool on0 = lane < PX, on1 = lane + 32 < PX;
+        for (int z = 0; z < PZ; z++) {
+            const unsigned gz = (unsigned)wrapc(z0 + z, geo.Nt[2], fw) * geo.Nt[1];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int y = warp + TI_WARPS * k;
+                if (y < PY) {
+                    const C* src = g + (gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
+                    C* dst = tile + (z * PY + y) * PX + lane;
+                    if (on0) cp_async_cell(dst, src + xg0);
+                    if (on1) cp_async_cell(dst + 32, src + xg1);
+                }
+            }
         }
     }
     if (threadIdx.x < lay.PN - PX * PY * PZ) tile[PX * PY * PZ + threadIdx.x] = make_c<T>(0, 0);
@@ -226,44 +231,72 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
             }
         };
         fetch(0, wx, wq, rq, rwu, base);
-        for (int n = 0; n < nn; n++) {
-            const C* p0 = tile + base;
-            T wx2[NWX], wq2[NIT], rq2 = 0, rwu2[VPC];
-            int base2 = base;
-            T sx = 0, sy = 0;
-            if (RG::FULL_IT == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, wq2, rq2, rwu2, base2);
+        // nodes are reduced in groups of 4: after two exchange steps each quarter-warp holds one node, so the
+        // 5-step butterfly costs 12 shuffles per 4 nodes instead of 40
+        for (int n4 = 0; n4 < nn; n4 += 4) {
+            T px[4], py[4];
 #pragma unroll
-            for (int it = 0; it < RG::FULL_IT; it++) {
-                const C* p = p0 + rowoff[it];
-                Unit<T> U[NV];
+            for (int q = 0; q < 4; q++) {
+                const int n = n4 + q;
+                T sx = 0, sy = 0;
+                if (n < nn) {
+                    const C* p0 = tile + base;
+                    T wx2[NWX], wq2[NIT], rq2 = 0, rwu2[VPC];
+                    int base2 = base;
+                    if (RG::FULL_IT == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, wq2, rq2, rwu2, base2);
 #pragma unroll
-                for (int u = 0; u < NV; u++) U[u].load(p + u * VPC);
-                if (it == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, wq2, rq2, rwu2, base2);
-                T a = 0, b = 0;
+                    for (int it = 0; it < RG::FULL_IT; it++) {
+                        const C* p = p0 + rowoff[it];
+                        Unit<T> U[NV];
 #pragma unroll
-                for (int u = 0; u < NV; u++) U[u].dot(&wx[u * VPC], a, b);
-                sx = tfma(wq[it], a, sx); sy = tfma(wq[it], b, sy);
-            }
-            if (RG::REM > 0 && rem_on) {
-                const C* p = p0 + rem_off;
-                T a = 0, b = 0;
-                if (RG::SPLIT) { Unit<T> U; U.load(p); U.dot(rwu, a, b); }
-                else {
+                        for (int u = 0; u < NV; u++) U[u].load(p + u * VPC);
+                        if (it == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, wq2, rq2, rwu2, base2);
+                        T a = 0, b = 0;
 #pragma unroll
-                    for (int u = 0; u < NV; u++) { Unit<T> U; U.load(p + u * VPC); U.dot(&wx[u * VPC], a, b); }
+                        for (int u = 0; u < NV; u++) U[u].dot(&wx[u * VPC], a, b);
+                        sx = tfma(wq[it], a, sx); sy = tfma(wq[it], b, sy);
+                    }
+                    if (RG::REM > 0 && rem_on) {
+                        const C* p = p0 + rem_off;
+                        T a = 0, b = 0;
+                        if (RG::SPLIT) { Unit<T> U; U.load(p); U.dot(rwu, a, b); }
+                        else {
+#pragma unroll
+                            for (int u = 0; u < NV; u++) { Unit<T> U; U.load(p + u * VPC); U.dot(&wx[u * VPC], a, b); }
+                        }
+                        sx = tfma(rq, a, sx); sy = tfma(rq, b, sy);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NWX; k++) wx[k] = wx2[k];
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) wq[it] = wq2[it];
+                    rq = rq2; base = base2;
+#pragma unroll
+                    for (int k = 0; k < VPC; k++) rwu[k] = rwu2[k];
                 }
-                sx = tfma(rq, a, sx); sy = tfma(rq, b, sy);
+                px[q] = sx; py[q] = sy;
             }
-            sx = warp_sum<T>(sx);
-            sy = warp_sum<T>(sy);
-            if (lane == 0) myres[n] = make_c<T>(sx, sy);
+            // exchange step 1 (xor 16): lower half keeps nodes {0,2}, upper half nodes {1,3}
+            const bool hi16 = lane & 16, hi8 = lane & 8;
+            T ax = hi16 ? px[1] : px[0], bx = hi16 ? px[0] : px[1];
+            T ay = hi16 ? py[1] : py[0], by = hi16 ? py[0] : py[1];
+            T cx = hi16 ? px[3] : px[2], dx = hi16 ? px[2] : px[3];
+            T cy = hi16 ? py[3] : py[2], dy = hi16 ? py[2] : py[3];
+            ax += __shfl_xor_sync(0xffffffffu, bx, 16); ay += __shfl_xor_sync(0xffffffffu, by, 16);
+            cx += __shfl_xor_sync(0xffffffffu, dx, 16); cy += __shfl_xor_sync(0xffffffffu, dy, 16);
+            // exchange step 2 (xor 8): quarter q = (lane>>3) holds node (hi16 ? 1 : 0) + 2*(hi8 ? 1 : 0)
+            T ex = hi8 ? cx : ax, fx = hi8 ? ax : cx;
+            T ey = hi8 ? cy : ay, fy = hi8 ? ay : cy;
+            ex += __shfl_xor_sync(0xffffffffu, fx, 8); ey += __shfl_xor_sync(0xffffffffu, fy, 8);
 #pragma unroll
-            for (int k = 0; k < NWX; k++) wx[k] = wx2[k];
-#pragma unroll
-            for (int it = 0; it < NIT; it++) wq[it] = wq2[it];
-            rq = rq2; base = base2;
-#pragma unroll
-            for (int k = 0; k < VPC; k++) rwu[k] = rwu2[k];
+            for (int o = 4; o > 0; o >>= 1) {
+                ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                ey += __shfl_xor_sync(0xffffffffu, ey, o);
+            }
+            if ((lane & 7) == 0) {
+                const int q = (hi16 ? 1 : 0) + (hi8 ? 2 : 0);
+                if (n4 + q < nn) myres[n4 + q] = make_c<T>(ex, ey);
+            }
         }
         __syncwarp();
         if (lane < nn) fhat[myint[2 * lane + 1]] = myres[lane];
@@ -278,7 +311,7 @@ int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, 
     GeomDev geo = make_geom<T>(p);
     InterpLayout<T, MT> lay(geo.bs);
     const size_t smem = lay.bytes();
-    if (smem > 227 * 1024) return -1;
+    if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
     auto kern = k_interp_row3d<T, MT>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(t_hi - t_lo, B);
@@ -300,7 +333,7 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
         explicit KernelTimer(nfftb200_plan* q) : p(q) { if (p->timing) cudaEventRecord(p->evk[3], p->stream); }
         ~KernelTimer() { if (p->timing) { cudaEventRecord(p->evk[4], p->stream); p->pending_k |= 2; } }
     } kt(p);
-    if (p->kernel_mode == 0 && is_complex && p->D == 3) {
+    if (p->kernel_mode != 1 && is_complex && p->D == 3) {
         int r = -1;
         switch (p->m) {
             case 2: r = launch_tile3d<T, 2>(p, g, fhat, B, t_lo, t_hi); break;

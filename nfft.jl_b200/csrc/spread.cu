@@ -104,9 +104,10 @@ template <typename T, int MT> struct SubLayout {
     }
 };
 
-template <typename T, int MT>
+template <typename T, int MT, bool SCRATCH>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>::type* __restrict__ g,
+               typename Cplx<T>::type* __restrict__ scratch,
                const T* __restrict__ xs, const int32_t* __restrict__ perm,
                const int32_t* __restrict__ tile_start, int tile_lo, long long M, GeomDev geo,
                WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp)
@@ -135,6 +136,10 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     const int ob0 = warp & 1, ob1 = (warp >> 1) & 1, ob2 = warp >> 2;
     fhat += (long long)blockIdx.y * M;
     g += (long long)blockIdx.y * geo.gsz;
+    if (SCRATCH) {
+        const int PXs = geo.bs[0] + L, PYs = geo.bs[1] + L, PZs = geo.bs[2] + L;
+        scratch += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)PXs * PYs * PZs);
+    }
     C* mysub = sub + warp * QN;
     T* myrec = rec_w + warp * 32 * RW;
     int* mybase = rec_b + warp * 32;
@@ -340,22 +345,100 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
             }
         }
         __syncthreads();
-        // flush: one vector RED (REDG.ADD.F32x2) per non-zero cell at the periodically wrapped position
+        // flush: one vector RED (REDG.ADD.F32x2) per non-zero cell at the periodically wrapped position;
+        // x-dependent quantities hoisted, (y,z) advance incrementally, no division
         const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
-        const unsigned inv = fastdiv_inv(PY);
-        for (int row = warp; row < PY * PZ; row += SS_WARPS) {
-            const int z = (int)fastdiv(row, inv), y = row - z * PY;
-            const int oy_ = y >= SY, oz_ = z >= SZ;
-            const C* pa = sub + (2 * oy_ + 4 * oz_) * QN + ((z - oz_ * SZ) * QY + (y - oy_ * SY)) * QX;
-            const unsigned ro = ((unsigned)wrapc(cz0 - MT + z, geo.Nt[2], fw) * geo.Nt[1] + wrapc(cy0 - MT + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
-            for (int x = lane; x < PX; x += 32) {
-                const C c = (x < SX) ? pa[x] : pa[QN + x - SX];
-                if (c.x != (T)0 || c.y != (T)0) red_add_c(g + ro + wrapc(cx0 - MT + x, geo.Nt[0], fw), c);
+        const int xa = lane, xb = lane + 32;
+        const bool on0 = xa < PX, on1 = xb < PX;
+        const int so0 = (xa < SX) ? xa : QN + xa - SX, so1 = (xb < SX) ? xb : QN + xb - SX;
+        const int xg0 = wrapc(cx0 - MT + xa, geo.Nt[0], fw), xg1 = wrapc(cx0 - MT + xb, geo.Nt[0], fw);
+        // every warp walks all z-planes and owns rows y = warp + 8k of each (k unrolled => independent
+        // address chains in flight; with one CTA per SM the ILP has to come from inside the warp)
+        for (int z = 0; z < PZ; z++) {
+            const int oz_ = z >= SZ;
+            const C* pz_ = sub + 4 * oz_ * QN + (z - oz_ * SZ) * QY * QX;
+            const unsigned gz = (unsigned)wrapc(cz0 - MT + z, geo.Nt[2], fw) * geo.Nt[1];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int y = warp + SS_WARPS * k;
+                if (y < PY) {
+                    const int oy_ = y >= SY;
+                    const C* pa = pz_ + 2 * oy_ * QN + (y - oy_ * SY) * QX;
+                    if (SCRATCH) {     // plain coalesced stores of the merged padded tile ("blocks[l]")
+                        C* sr = scratch + (z * PY + y) * PX;
+                        if (on0) sr[xa] = pa[so0];
+                        if (on1) sr[xb] = pa[so1];
+                    } else {
+                        C* gr = g + (gz + wrapc(cy0 - MT + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
+                        if (on0) { const C c = pa[so0]; if (c.x != (T)0 || c.y != (T)0) red_add_c(gr + xg0, c); }
+                        if (on1) { const C c = pa[so1]; if (c.x != (T)0 || c.y != (T)0) red_add_c(gr + xg1, c); }
+                    }
+                }
             }
         }
     }
 }
 
+// addBlock! without the lock (/root/reference/src/convolution.jl:371-443): every grid cell sums, in a fixed
+// order, the <= 8 padded tiles that cover it and is written exactly once (so no memset of g either).
+// Preconditions checked on the host: every tile core is at least m cells long in every dimension.
+// One thread per 16-byte unit of the grid; (u1,u2) are block-uniform.
+template <typename T, int MT>
+__global__ void __launch_bounds__(256)
+k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cplx<T>::type* __restrict__ g,
+                 const int32_t* __restrict__ tile_start, int tile_lo, int tile_hi, GeomDev geo)
+{
+    using C = typename Cplx<T>::type;
+    constexpr int L = 2 * MT, VPC = 16 / (int)sizeof(C);
+    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
+    const size_t PN = (size_t)PX * PY * PZ;
+    const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * VPC;
+    const int u1 = blockIdx.y, u2 = blockIdx.z % geo.Nt[2], b = blockIdx.z / geo.Nt[2];
+    if (u0 >= geo.Nt[0]) return;
+    scratch += (size_t)b * (tile_hi - tile_lo) * PN;
+    // per dimension: the (tile, padded coordinate) pairs that cover cell u
+    auto cover = [&](int u, int d, int (&tt)[3], int (&pp)[3]) -> int {
+        const int bs = geo.bs[d], nb = geo.nb[d], Nt = geo.Nt[d];
+        const int t = u / bs, l = u - t * bs;
+        const int len = (t == nb - 1) ? Nt - t * bs : bs;
+        int n = 0;
+        tt[n] = t; pp[n] = l + MT; n++;
+        if (l < MT) {                                   // high halo of the previous tile
+            const int tp = t == 0 ? nb - 1 : t - 1;
+            const int lenp = (tp == nb - 1) ? Nt - tp * bs : bs;
+            tt[n] = tp; pp[n] = l + MT + lenp; n++;
+        }
+        if (l >= len - MT) {                            // low halo of the next tile
+            tt[n] = t == nb - 1 ? 0 : t + 1; pp[n] = l + MT - len; n++;
+        }
+        return n;
+    };
+    int ty[3], py[3], tz[3], pz[3];
+    const int ny = cover(u1, 1, ty, py), nz = cover(u2, 2, tz, pz);
+    C acc[VPC];
+#pragma unroll
+    for (int k = 0; k < VPC; k++) acc[k] = make_c<T>(0, 0);
+#pragma unroll
+    for (int k = 0; k < VPC; k++) {
+        int tx[3], px[3];
+        const int nx = cover(u0 + k, 0, tx, px);
+        for (int iz = 0; iz < nz; iz++)
+            for (int iy = 0; iy < ny; iy++)
+                for (int ix = 0; ix < nx; ix++) {
+                    const int tile = (tz[iz] * geo.nb[1] + ty[iy]) * geo.nb[0] + tx[ix];
+                    if (tile < tile_lo || tile >= tile_hi) continue;
+                    if (tile_start[tile + 1] == tile_start[tile]) continue;        // empty tile: never written
+                    const C c = scratch[(size_t)(tile - tile_lo) * PN + ((size_t)pz[iz] * PY + py[iy]) * PX + px[ix]];
+                    acc[k].x += c.x; acc[k].y += c.y;
+                }
+    }
+    C* dst = g + (size_t)b * geo.gsz + ((size_t)u2 * geo.Nt[1] + u1) * geo.Nt[0] + u0;
+    if (VPC == 2) *reinterpret_cast<float4*>(dst) = make_float4((float)acc[0].x, (float)acc[0].y, (float)acc[VPC - 1].x, (float)acc[VPC - 1].y);
+    else dst[0] = acc[0];
+}
+
+// returns -1 if the tiled kernel does not apply, else a status; *wrote_all = true if every grid cell was
+// written by the gather pass (no memset needed)
 template <typename T, int MT>
 int launch_tile3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi)
 {
@@ -363,14 +446,53 @@ int launch_tile3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, 
     GeomDev geo = make_geom<T>(p);
     SubLayout<T, MT> lay(geo.bs);
     const size_t smem = lay.bytes();
-    if (smem > 227 * 1024) return -1;
-    auto kern = k_spread_sub3d<T, MT>;
-    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
+    bool use_scratch = p->kernel_mode != 2;
+    for (int d = 0; d < 3; d++) {
+        const int last = geo.Nt[d] - (geo.nb[d] - 1) * geo.bs[d];
+        if (geo.bs[d] < MT || last < MT) use_scratch = false;        // halos would reach past the neighbour
+    }
+    const size_t PN = (size_t)(geo.bs[0] + 2 * MT) * (geo.bs[1] + 2 * MT) * (geo.bs[2] + 2 * MT);
+    const cudaStream_t st = p->stream;
     dim3 grid(t_hi - t_lo, B);
-    kern<<<grid, SS_THREADS, smem, p->stream>>>((const C*)fhat, (C*)g, (const T*)p->d_xs, p->d_perm,
-                                               p->d_tile_start, t_lo, p->M, geo, make_win<T>(p),
-                                               make_poly_param<T, MT>(p));
-    p->launches++;
+    if (use_scratch) {
+        const int64_t need = (int64_t)(sizeof(C) * PN * (size_t)(t_hi - t_lo) * B);
+        if (need > p->cap_tilebuf) {
+            if (p->d_tilebuf) cudaFree(p->d_tilebuf);
+            p->d_tilebuf = nullptr; p->cap_tilebuf = 0;
+            if (cudaMalloc(&p->d_tilebuf, (size_t)need) != cudaSuccess) { cudaGetLastError(); use_scratch = false; }
+            else p->cap_tilebuf = need;
+        }
+    }
+    struct KT {
+        nfftb200_plan* p;
+        explicit KT(nfftb200_plan* q) : p(q) { if (p->timing) cudaEventRecord(p->evk[1], p->stream); }
+        ~KT() { if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; } }
+    };
+    if (use_scratch) {
+        if (p->timing) cudaEventRecord(p->evk[0], st);
+        KT kt(p);
+        auto kern = k_spread_sub3d<T, MT, true>;
+        CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SS_THREADS, smem, st>>>((const C*)fhat, (C*)g, (C*)p->d_tilebuf, (const T*)p->d_xs, p->d_perm,
+                                            p->d_tile_start, t_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
+        constexpr int VPC = 16 / (int)sizeof(C);
+        const int units = (geo.Nt[0] + VPC - 1) / VPC;
+        int bx = 32;
+        while (bx < 256 && bx < units) bx <<= 1;
+        dim3 gg((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);
+        k_gather_tiles3d<T, MT><<<gg, bx, 0, st>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_start, t_lo, t_hi, geo);
+        p->launches += 2;
+    } else {
+        if (p->timing) cudaEventRecord(p->evk[0], st);
+        CUDA_TRY(p, cudaMemsetAsync(g, 0, sizeof(C) * (size_t)p->gsz * B, st));
+        KT kt(p);
+        auto kern = k_spread_sub3d<T, MT, false>;
+        CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SS_THREADS, smem, st>>>((const C*)fhat, (C*)g, nullptr, (const T*)p->d_xs, p->d_perm,
+                                            p->d_tile_start, t_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
+        p->launches += 2;
+    }
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;
 }
@@ -379,18 +501,8 @@ template <typename T>
 int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_complex, int t_lo, int t_hi,
                 long long i_lo, long long i_hi)
 {
-    // zero the grid (memset(g), /root/reference/src/convolution.jl:358)
     const size_t cell = is_complex ? 2 * sizeof(T) : sizeof(T);
-    if (p->timing) cudaEventRecord(p->evk[0], p->stream);
-    CUDA_TRY(p, cudaMemsetAsync(g, 0, cell * (size_t)p->gsz * B, p->stream));
-    p->launches++;
-    if (i_hi <= i_lo) return NFFTB200_OK;
-    struct KernelTimer {
-        nfftb200_plan* p;
-        explicit KernelTimer(nfftb200_plan* q) : p(q) { if (p->timing) cudaEventRecord(p->evk[1], p->stream); }
-        ~KernelTimer() { if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; } }
-    } kt(p);
-    if (p->kernel_mode == 0 && is_complex && p->D == 3) {
+    if (i_hi > i_lo && p->kernel_mode != 1 && is_complex && p->D == 3) {
         int r = -1;
         switch (p->m) {
             case 2: r = launch_tile3d<T, 2>(p, fhat, g, B, t_lo, t_hi); break;
@@ -402,6 +514,16 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
         }
         if (r >= 0) return r;
     }
+    // generic path: zero the grid (memset(g), /root/reference/src/convolution.jl:358), then global REDs
+    if (p->timing) cudaEventRecord(p->evk[0], p->stream);
+    CUDA_TRY(p, cudaMemsetAsync(g, 0, cell * (size_t)p->gsz * B, p->stream));
+    p->launches++;
+    if (i_hi <= i_lo) return NFFTB200_OK;
+    struct KernelTimer {
+        nfftb200_plan* p;
+        explicit KernelTimer(nfftb200_plan* q) : p(q) { if (p->timing) cudaEventRecord(p->evk[1], p->stream); }
+        ~KernelTimer() { if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; } }
+    } kt(p);
     const long long n = i_hi - i_lo;
     const int blocks = (int)std::min<long long>((n + 7) / 8, 148 * 32);
     if (is_complex)

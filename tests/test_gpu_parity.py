@@ -64,7 +64,7 @@ def test_permutation_custom_block_size(nb, bs):
 @pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14), (32, 32, 32)])
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("pre", [O.POLYNOMIAL, O.LINEAR, O.FULL, O.TENSOR])
-@pytest.mark.parametrize("kernel_mode", [0, 1])
+@pytest.mark.parametrize("kernel_mode", [0, 1, 2])
 def test_forward_adjoint_vs_oracle(nb, N, T, pre, kernel_mode):
     D = len(N)
     M = int(np.prod(N))
