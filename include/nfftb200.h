@@ -146,6 +146,9 @@ int nfftb200_sync(nfftb200_plan* p);
  * ncclReduceScatter over slabs of the last grid dim -> slab FFT; forward = slab FFT ->
  * ncclAllGather -> local interpolation). */
 int nfftb200_comm_unique_id(void* out128);
+/* host logic of the node sharding: tile-aligned cut of the sorted node list into nranks ranges of ~M/nranks
+ * nodes; tile_start has ntiles+1 prefix sums, out receives nranks+1 tile boundaries */
+int nfftb200_partition_tiles(const int64_t* tile_start, int64_t ntiles, int nranks, int64_t* out);
 int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, int nranks, int mode);
 
 const char* nfftb200_last_error(nfftb200_plan* p);

@@ -4,7 +4,8 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libnfftb200.so"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ ${NFFTB_EXTRA_FLAGS}"
+NCCL_INC=${NCCL_INC:-/usr/include}
+FLAGS="-I$NCCL_INC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ ${NFFTB_EXTRA_FLAGS}"
 mkdir -p "$HERE/_obj"
 pids=()
 for f in plan.cu sort.cu deconv.cu spread.cu interp.cu comm.cu; do

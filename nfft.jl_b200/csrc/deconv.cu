@@ -6,6 +6,8 @@
 //            -- deconvolve_transpose!, /root/reference/src/deconvolution.jl:69-92.
 // n_d = i_d - N_d/2 (integer division) for image index i_d in [0, N_d); multiplication order
 // ((f*L1)*L2)*L3 as in the reference.  HBM-bound: 2s*(prod N + prod Nt)*B bytes per call.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -95,6 +97,60 @@ k_deconv_adj(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::typ
     }
 }
 
+// ---- slab variants for the node-sharded multi-GPU path (comm.cu).  The transposed slab holds, for the grid
+// dimension D-2 ("mid"), only the range [mid_off, mid_off + Ms); layout [outer = dim D-1][Ms][inner = dims < D-2].
+template <typename T>
+__global__ void k_slab_deconv_fwd(const typename Cplx<T>::type* __restrict__ f, typename Cplx<T>::type* __restrict__ slab,
+                                  GeomDev geo, const T* __restrict__ lut, int mid_off, int Ms)
+{
+    using C = typename Cplx<T>::type;
+    const int D = geo.D;
+    const long long inner = D == 3 ? geo.Nt[0] : 1;
+    const long long n = inner * Ms * geo.Nt[D - 1];
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % inner);
+        long long r = e / inner;
+        const int ml = (int)(r % Ms);
+        const int o = (int)(r / Ms);
+        int u[3] = {0, 0, 0};
+        if (D == 3) { u[0] = i; u[1] = mid_off + ml; u[2] = o; } else { u[0] = mid_off + ml; u[1] = o; }
+        C v = make_c<T>(0, 0);
+        int idx[3] = {0, 0, 0};
+        bool in = true;
+        for (int d = 0; d < D; d++) { idx[d] = img_index(u[d], geo.N[d], geo.Nt[d]); in = in && idx[d] >= 0; }
+        if (in) {
+            v = f[((long long)idx[2] * geo.N[1] + idx[1]) * geo.N[0] + idx[0]];
+            int lo = 0;
+            for (int d = 0; d < D; d++) { const T s = lut[lo + idx[d]]; v.x *= s; v.y *= s; lo += geo.N[d]; }
+        }
+        slab[e] = v;
+    }
+}
+
+template <typename T>
+__global__ void k_slab_deconv_adj(const typename Cplx<T>::type* __restrict__ slab, typename Cplx<T>::type* __restrict__ f,
+                                  GeomDev geo, const T* __restrict__ lut, int mid_off, int Ms)
+{
+    using C = typename Cplx<T>::type;
+    const int D = geo.D;
+    const long long inner = D == 3 ? geo.Nt[0] : 1;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < geo.fsz; e += (long long)gridDim.x * blockDim.x) {
+        int idx[3];
+        long long r = e;
+        idx[0] = (int)(r % geo.N[0]); r /= geo.N[0];
+        idx[1] = (int)(r % geo.N[1]); idx[2] = (int)(r / geo.N[1]);
+        int u[3] = {0, 0, 0};
+        for (int d = 0; d < D; d++) u[d] = grid_index(idx[d], geo.N[d], geo.Nt[d]);
+        const int um = u[D - 2] - mid_off;
+        if (um < 0 || um >= Ms) continue;                         // another rank owns this part of the image
+        const long long se = ((long long)u[D - 1] * Ms + um) * inner + (D == 3 ? u[0] : 0);
+        C v = slab[se];
+        int lo = 0;
+        for (int d = 0; d < D; d++) { const T s = lut[lo + idx[d]]; v.x *= s; v.y *= s; lo += geo.N[d]; }
+        f[e] = v;
+    }
+}
+
 inline void launch_dims(int n0, int n1, int n2, dim3& grid, dim3& block)
 {
     int bx = 32;
@@ -128,6 +184,30 @@ template <typename T> int deconv_impl(nfftb200_plan* p, const void* src, void* d
 }
 
 }  // namespace
+
+int nfftb_slab_deconvolve(nfftb200_plan* p, const void* d_f, void* d_slab, int64_t mid_off, int64_t Ms)
+{
+    const long long n = p->gsz / p->nranks;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 32);
+    if (p->dtype == NFFTB200_F32)
+        k_slab_deconv_fwd<float><<<blocks, 256, 0, p->stream>>>((const float2*)d_f, (float2*)d_slab, make_geom<float>(p), (const float*)p->d_hat_inv, (int)mid_off, (int)Ms);
+    else
+        k_slab_deconv_fwd<double><<<blocks, 256, 0, p->stream>>>((const double2*)d_f, (double2*)d_slab, make_geom<double>(p), (const double*)p->d_hat_inv, (int)mid_off, (int)Ms);
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+int nfftb_slab_deconvolve_transpose(nfftb200_plan* p, const void* d_slab, void* d_f, int64_t mid_off, int64_t Ms)
+{
+    const int blocks = (int)std::min<long long>((p->fsz + 255) / 256, 148 * 32);
+    if (p->dtype == NFFTB200_F32)
+        k_slab_deconv_adj<float><<<blocks, 256, 0, p->stream>>>((const float2*)d_slab, (float2*)d_f, make_geom<float>(p), (const float*)p->d_hat_inv, (int)mid_off, (int)Ms);
+    else
+        k_slab_deconv_adj<double><<<blocks, 256, 0, p->stream>>>((const double2*)d_slab, (double2*)d_f, make_geom<double>(p), (const double*)p->d_hat_inv, (int)mid_off, (int)Ms);
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
 
 int nfftb_deconvolve(nfftb200_plan* p, const void* d_f, void* d_g, int B)
 {

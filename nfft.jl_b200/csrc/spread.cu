@@ -396,41 +396,47 @@ k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cp
     const int u1 = blockIdx.y, u2 = blockIdx.z % geo.Nt[2], b = blockIdx.z / geo.Nt[2];
     if (u0 >= geo.Nt[0]) return;
     scratch += (size_t)b * (tile_hi - tile_lo) * PN;
-    // per dimension: the (tile, padded coordinate) pairs that cover cell u
-    auto cover = [&](int u, int d, int (&tt)[3], int (&pp)[3]) -> int {
+    // per dimension: the (tile, padded coordinate) pairs that cover cell u; packed as tile*stride + p offsets
+    // so that the inner loops are pure adds.  Offsets are in cells of the scratch buffer.
+    auto cover = [&](int u, int d, unsigned inv, size_t tstride, size_t pstride, size_t (&off)[3], int (&tid)[3], int tmul) -> int {
         const int bs = geo.bs[d], nb = geo.nb[d], Nt = geo.Nt[d];
-        const int t = u / bs, l = u - t * bs;
+        const int t = (int)fastdiv((unsigned)u, inv), l = u - t * bs;
         const int len = (t == nb - 1) ? Nt - t * bs : bs;
         int n = 0;
-        tt[n] = t; pp[n] = l + MT; n++;
+        tid[n] = t * tmul; off[n] = (size_t)(l + MT) * pstride; n++;
         if (l < MT) {                                   // high halo of the previous tile
             const int tp = t == 0 ? nb - 1 : t - 1;
             const int lenp = (tp == nb - 1) ? Nt - tp * bs : bs;
-            tt[n] = tp; pp[n] = l + MT + lenp; n++;
+            tid[n] = tp * tmul; off[n] = (size_t)(l + MT + lenp) * pstride; n++;
         }
         if (l >= len - MT) {                            // low halo of the next tile
-            tt[n] = t == nb - 1 ? 0 : t + 1; pp[n] = l + MT - len; n++;
+            tid[n] = (t == nb - 1 ? 0 : t + 1) * tmul; off[n] = (size_t)(l + MT - len) * pstride; n++;
         }
         return n;
     };
-    int ty[3], py[3], tz[3], pz[3];
-    const int ny = cover(u1, 1, ty, py), nz = cover(u2, 2, tz, pz);
+    size_t oy[3], oz[3], ox[3];
+    int ty[3], tz[3], tx[3];
+    const int ny = cover(u1, 1, fastdiv_inv(geo.bs[1]), 0, (size_t)PX, oy, ty, geo.nb[0]);
+    const int nz = cover(u2, 2, fastdiv_inv(geo.bs[2]), 0, (size_t)PX * PY, oz, tz, geo.nb[0] * geo.nb[1]);
+    const unsigned invx = fastdiv_inv(geo.bs[0]);
     C acc[VPC];
 #pragma unroll
     for (int k = 0; k < VPC; k++) acc[k] = make_c<T>(0, 0);
 #pragma unroll
     for (int k = 0; k < VPC; k++) {
-        int tx[3], px[3];
-        const int nx = cover(u0 + k, 0, tx, px);
+        const int nx = cover(u0 + k, 0, invx, 0, 1, ox, tx, 1);
         for (int iz = 0; iz < nz; iz++)
-            for (int iy = 0; iy < ny; iy++)
+            for (int iy = 0; iy < ny; iy++) {
+                const int tyz = tz[iz] + ty[iy];
+                const size_t oyz = oz[iz] + oy[iy];
                 for (int ix = 0; ix < nx; ix++) {
-                    const int tile = (tz[iz] * geo.nb[1] + ty[iy]) * geo.nb[0] + tx[ix];
+                    const int tile = tyz + tx[ix];
                     if (tile < tile_lo || tile >= tile_hi) continue;
                     if (tile_start[tile + 1] == tile_start[tile]) continue;        // empty tile: never written
-                    const C c = scratch[(size_t)(tile - tile_lo) * PN + ((size_t)pz[iz] * PY + py[iy]) * PX + px[ix]];
+                    const C c = scratch[(size_t)(tile - tile_lo) * PN + oyz + ox[ix]];
                     acc[k].x += c.x; acc[k].y += c.y;
                 }
+            }
     }
     C* dst = g + (size_t)b * geo.gsz + ((size_t)u2 * geo.Nt[1] + u1) * geo.Nt[0] + u0;
     if (VPC == 2) *reinterpret_cast<float4*>(dst) = make_float4((float)acc[0].x, (float)acc[0].y, (float)acc[VPC - 1].x, (float)acc[VPC - 1].y);

@@ -132,7 +132,7 @@ class B200NFFTPlan:
     def __init__(self, k, N, *, m=None, σ=None, sigma=None, reltol=None, window="kaiser_bessel",
                  precompute=POLYNOMIAL, ntransforms=1, blockSize=None, dims=None, device=None,
                  sortNodes=False, storeDeconvolutionIdx=False, blocking=True, fftflags=None,
-                 LUTSize=0, timing=None, stream="current"):
+                 LUTSize=0, timing=None, stream="current", shard=None, process_group=None):
         t0 = time.perf_counter()
         if σ is None:
             σ = sigma
@@ -167,6 +167,19 @@ class B200NFFTPlan:
         self.N = N
         self.D = D
         self.dims = range(1, D + 1)
+        # ---- multi-GPU (one process per GPU): shard = None | "batch" | "nodes"
+        self.shard = shard
+        self.rank, self.world = 0, 1
+        self.global_ntransforms = int(ntransforms)
+        if shard is not None:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(process_group), dist.get_world_size(process_group)
+            if shard == "batch":
+                lo, hi = shard_batch(int(ntransforms), self.rank, self.world)
+                self.batch_range = (lo, hi)
+                ntransforms = hi - lo
+            elif shard != "nodes":
+                raise ArgumentError("shard must be None, 'batch' or 'nodes'")
         self.ntransforms = int(ntransforms)
         self._h = C.c_void_p()
         Narr = (C.c_int64 * D)(*N)
@@ -190,6 +203,10 @@ class B200NFFTPlan:
         self.J = 0
         self.NOut = (0,)
         self.k = None
+        if shard == "nodes" and self.world > 1:
+            self.comm_init(broadcast_unique_id(self._L, self.rank, process_group, self.device), self.rank, self.world, 2)
+        elif shard == "batch":
+            _check(self._h, self._L.nfftb200_comm_init(self._h, None, self.rank, self.world, 1))
         self.nodes_(k)
         if timing is not None:
             timing.pre = time.perf_counter() - t0                      # src/NFFT.jl:51-56
@@ -591,6 +608,38 @@ def nfft_adjoint(k, N, fHat, **kw):
     """derived.jl:147-153"""
     p = plan_nfft(k, N, **kw)
     return p.adjoint() * fHat
+
+
+# ---- multi-GPU helpers --------------------------------------------------------------------------------
+def shard_batch(B, rank, world):
+    """transforms [lo, hi) owned by `rank` under batch sharding"""
+    if B % world:
+        raise ArgumentError(f"ntransforms={B} is not divisible by the number of ranks {world}")
+    per = B // world
+    return rank * per, (rank + 1) * per
+
+
+def partition_tiles(tile_start, nranks):
+    """tile-aligned node ranges for node sharding; returns nranks+1 tile boundaries"""
+    ts = np.ascontiguousarray(tile_start, dtype=np.int64)
+    out = np.empty(nranks + 1, dtype=np.int64)
+    st = _lib.lib().nfftb200_partition_tiles(ts.ctypes.data_as(C.c_void_p), ts.size - 1, int(nranks),
+                                             out.ctypes.data_as(C.c_void_p))
+    _check(None, st)
+    return out
+
+
+def broadcast_unique_id(L, rank, process_group=None, device=0):
+    """rank 0 creates the 128-byte ncclUniqueId, torch.distributed carries it to the other ranks"""
+    import torch.distributed as dist
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _check(None, L.nfftb200_comm_unique_id(buf))
+    backend = dist.get_backend(process_group)
+    dev = f"cuda:{device}" if "nccl" in str(backend) else "cpu"
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=process_group)
+    return bytes(t.cpu().tolist())
 
 
 # ---- helpers ----------------------------------------------------------------------------------------
