@@ -151,7 +151,11 @@ def main():
     N, M, T = w["N"], w["M"], w["T"]
     k = O.random_nodes(M, 3, T, seed=1)                     # same nodes on every rank (shared by the batch)
     kd = torch.from_numpy(np.ascontiguousarray(k.T)).cuda()
-    p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"])
+    if world > 1:      # batched plan with ntransforms = world, one transform per rank, no data-path collective
+        p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"], ntransforms=world, shard="batch")
+        assert p.ntransforms == 1
+    else:
+        p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"])
     p.set_kernel_mode(args.kernel_mode)
     f_h = O.random_complex(N, T, 100 + rank)
     fh_h = O.random_complex(M, T, 200 + rank)
@@ -242,12 +246,12 @@ def main():
             traffic = json.load(fh_).get("spread_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_spread_tile3d<float,3> (adjoint gridding)",
+    roofline = {"bound": "hbm", "kernel": "adjoint gridding: k_spread_sub3d<float,3> + k_gather_tiles3d (convolve_transpose!)",
                 "achieved": abytes / t_spread / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": abytes / t_spread / 1e9 / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": abytes, "us_per_launch": t_spread * 1e6,
                 "note": "3-D spreading is shared-memory-bound (216 complex RMWs/node); HBM fraction is the contract metric",
-                "interp": {"kernel": "k_interp_tile3d<float,3>", "achieved": abytes / t_interp / 1e9,
+                "interp": {"kernel": "k_interp_row3d<float,3> (convolve!)", "achieved": abytes / t_interp / 1e9,
                            "frac": abytes / t_interp / 1e9 / peak, "us_per_launch": t_interp * 1e6}}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
