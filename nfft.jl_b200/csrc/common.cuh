@@ -12,6 +12,7 @@
 
 #define NFFTB_MAX_D 3
 #define NFFTB_MAX_M 8            // taps per dim = 2m <= 16
+#define NFFTB_G1D 256            // cells per CTA of the 1-D output-stationary spreader
 
 // ---------------------------------------------------------------------------------------
 // complex value types
@@ -94,6 +95,7 @@ struct nfftb200_plan {
     int32_t* d_tile_start = nullptr; // ntiles + 1
     std::vector<int32_t> h_tile_start;  // host copy (tile-aligned sharding, launch ranges)
     int64_t cap_nodes = 0;
+    int max_neigh_1d = 0;            // 1-D: max nodes a tile's output-stationary spreader must bucket
 
     // sort scratch
     uint32_t* d_keys[2] = {nullptr, nullptr};
@@ -194,4 +196,6 @@ int nfftb_spread(nfftb200_plan* p, const void* d_fhat, void* d_g, int B, int is_
 int nfftb_interp(nfftb200_plan* p, const void* d_g, void* d_fhat, int B, int is_complex,
                  int64_t t_lo, int64_t t_hi);                                   // interp.cu
 int nfftb_build_tables(nfftb200_plan* p);
-size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs);                // spread.cu                                       // tables.cpp
+size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs);                // spread.cu
+int nfftb_spread_1d(nfftb200_plan* p, const void* fhat, void* g, int B, int is_complex, int t_lo, int t_hi);   // oned.cu
+int nfftb_interp_1d(nfftb200_plan* p, const void* g, void* fhat, int B, int is_complex, long long i_lo, long long i_hi);                                       // tables.cpp

@@ -333,6 +333,10 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
         explicit KernelTimer(nfftb200_plan* q) : p(q) { if (p->timing) cudaEventRecord(p->evk[3], p->stream); }
         ~KernelTimer() { if (p->timing) { cudaEventRecord(p->evk[4], p->stream); p->pending_k |= 2; } }
     } kt(p);
+    if (p->kernel_mode != 1 && p->D == 1) {
+        const int r = nfftb_interp_1d(p, g, fhat, B, is_complex, i_lo, i_hi);
+        if (r >= 0) return r;
+    }
     if (p->kernel_mode != 1 && is_complex && p->D == 3) {
         int r = -1;
         switch (p->m) {

@@ -1,0 +1,266 @@
+// oned.cu -- 1-D kernels (D = 1; BASELINE config C4: N = 2^22, M = 2^25, Float64, ~4 nodes per grid cell).
+//
+//  * k_spread_1d: OUTPUT-STATIONARY adjoint gridding.  One CTA per reference tile (blockSize cells).  The tile's
+//    nodes are bucketed by grid cell in shared memory (counting sort; the stable order inside a cell is restored
+//    with a rank by original position, so the summation order is deterministic).  Then every thread owns ONE
+//    grid cell of the tile, keeps its accumulator in registers and, for each of the 2m taps l, walks the nodes of
+//    cell u + m - 1 - l and adds w_l(frac) * fHat.  The number of (node, tap) pairs is exactly the reference's
+//    (2m per node, /root/reference/src/convolution.jl:465-492); there is no read-modify-write, no atomic, no
+//    memset: each grid cell is written once.  Neighbour tiles' boundary nodes are read through the same buckets
+//    (halo of m cells on each side, periodic).
+//  * k_interp_1d: thread per node, weights in registers, 2m loads from the (L1/L2-resident) grid.
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+#include "tile3d.cuh"
+#include "window.cuh"
+
+namespace {
+
+constexpr int O1_THREADS = 256;
+
+// Nodes relevant to a tile: those with cell c in [t0 - m, t0 + bs + m - 1) (periodic).  They live in up to three
+// contiguous sorted ranges (previous tile's tail cells, own tile, next tile's head cells); since nodes are only
+// sorted by tile, the neighbour tiles are scanned completely and filtered by cell.
+template <typename T, int MT, bool CPLX>
+__global__ void __launch_bounds__(O1_THREADS)
+k_spread_1d(const void* __restrict__ fhat_, void* __restrict__ g_, const T* __restrict__ xs,
+            const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_start, int tile_lo, int tile_hi,
+            long long M, GeomDev geo, WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp, int cap, int S)
+{
+    using C = typename Cplx<T>::type;
+    using V = typename std::conditional<CPLX, C, T>::type;
+    constexpr int L = 2 * MT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int bs = geo.bs[0], Nt = geo.Nt[0], nb = geo.nb[0];
+    const int W = NFFTB_G1D + L;                           // bucketed cells: [u0 - m, u0 + G + m) of the sub-block
+    int* cnt = reinterpret_cast<int*>(smem_raw);           // [W + 1] counts -> offsets
+    int* fill = cnt + W + 1;                               // [W]
+    const size_t head = (sizeof(int) * (size_t)(2 * W + 1) + 15) & ~(size_t)15;
+    V* s_v = reinterpret_cast<V*>(smem_raw + head);        // [cap] node values
+    T* s_t = reinterpret_cast<T*>(s_v + cap);              // [cap] frac - 1/2 (POLYNOMIAL) or frac + m - 1
+    int* s_i = reinterpret_cast<int*>(s_t + cap);          // [cap] sorted position (restores a stable order)
+
+    const int tile = blockIdx.x / S, sub = blockIdx.x - tile * S;
+    const int tlen = min(bs, Nt - tile * bs);              // core length of the tile
+    if (sub * NFFTB_G1D >= tlen) return;
+    const int t0 = tile * bs + sub * NFFTB_G1D;            // first cell of this sub-block
+    const int len = min(NFFTB_G1D, tlen - sub * NFFTB_G1D);
+    const int b = blockIdx.y;
+    const V* fhat = reinterpret_cast<const V*>(fhat_) + (long long)b * M;
+    V* g = reinterpret_cast<V*>(g_) + (long long)b * geo.gsz;
+
+    const int tp = tile == 0 ? nb - 1 : tile - 1, tn = tile == nb - 1 ? 0 : tile + 1;
+    auto in_range = [&](int t) { return t >= tile_lo && t < tile_hi; };
+    // candidate ranges (sorted positions); a tile that is its own neighbour (nb <= 2) is visited once
+    int r_lo[3], r_hi[3], nr = 0;
+    const bool need_p = sub * NFFTB_G1D - MT < 0, need_n = sub * NFFTB_G1D + len + MT - 2 >= tlen;
+    if (in_range(tile)) { r_lo[nr] = tile_start[tile]; r_hi[nr] = tile_start[tile + 1]; nr++; }
+    if (need_p && tp != tile && in_range(tp)) { r_lo[nr] = tile_start[tp]; r_hi[nr] = tile_start[tp + 1]; nr++; }
+    if (need_n && tn != tile && !(need_p && tn == tp) && in_range(tn)) { r_lo[nr] = tile_start[tn]; r_hi[nr] = tile_start[tn + 1]; nr++; }
+
+    // bucket index of a node cell c relative to this tile, or -1 (periodic distance, window [-m, len + m - 1))
+    auto bucket = [&](int c) {
+        int d = c - t0;
+        if (d >= Nt - MT) d -= Nt;                         // wrapped from the left neighbour
+        if (d < -MT) d += Nt;                              // wrapped from the right neighbour
+        return (d >= -MT && d <= len + MT - 2) ? d + MT : -1;
+    };
+
+    for (int q = threadIdx.x; q <= W; q += O1_THREADS) cnt[q] = 0;
+    __syncthreads();
+    // pass 1: count
+    for (int r = 0; r < nr; r++)
+        for (int i = r_lo[r] + threadIdx.x; i < r_hi[r]; i += O1_THREADS) {
+            T ks;
+            const int bk = bucket(node_cell<T>(xs[i], Nt, ks));
+            if (bk >= 0) atomicAdd(&cnt[bk + 1], 1);
+        }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                // inclusive scan of cnt[0..W] by the first warp
+        int carry = 0;
+        for (int base = 0; base <= W; base += 32) {
+            const int q = base + threadIdx.x;
+            int v = q <= W ? cnt[q] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if ((int)threadIdx.x >= o) v += t; }
+            if (q <= W) cnt[q] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    const int total = cnt[W];
+    for (int q = threadIdx.x; q < W; q += O1_THREADS) fill[q] = 0;
+    __syncthreads();
+    const bool fits = total <= cap;
+    if (fits) {
+        // pass 2: scatter (order inside a bucket is arbitrary here, fixed up below by sorting on s_i)
+        for (int r = 0; r < nr; r++)
+            for (int i = r_lo[r] + threadIdx.x; i < r_hi[r]; i += O1_THREADS) {
+                T ks;
+                const int c = node_cell<T>(xs[i], Nt, ks);
+                const int bk = bucket(c);
+                if (bk >= 0) {
+                    const int pos = cnt[bk] + atomicAdd(&fill[bk], 1);
+                    const int off = c - MT + 1;
+                    const T d0 = sub_rn(ks, (T)off);
+                    // POLYNOMIAL: frac - 1/2 (evalpoly argument); otherwise keep d0 = frac + m - 1
+                    s_t[pos] = (win.mode == NFFTB200_POLYNOMIAL) ? sub_rn(add_rn(sub_rn(d0, (T)MT), (T)1), (T)0.5) : d0;
+                    s_v[pos] = fhat[perm[i]];
+                    s_i[pos] = i;
+                }
+            }
+        __syncthreads();
+        // restore ascending sorted position inside every bucket (insertion sort; buckets hold a handful of nodes)
+        for (int q = threadIdx.x; q < W; q += O1_THREADS) {
+            const int a = cnt[q], e = cnt[q + 1];
+            for (int x = a + 1; x < e; x++) {
+                const int ki = s_i[x]; const T kt = s_t[x]; const V kv = s_v[x];
+                int y = x - 1;
+                while (y >= a && s_i[y] > ki) { s_i[y + 1] = s_i[y]; s_t[y + 1] = s_t[y]; s_v[y + 1] = s_v[y]; y--; }
+                s_i[y + 1] = ki; s_t[y + 1] = kt; s_v[y + 1] = kv;
+            }
+        }
+        __syncthreads();
+    }
+    // gather: thread u owns grid cell t0 + u
+    for (int u = threadIdx.x; u < len; u += O1_THREADS) {
+        T ax = 0, ay = 0;
+        if (fits) {
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                // tap l of a node in cell c hits cell c - m + 1 + l  =>  c = u + m - 1 - l, bucket = c - t0 + m
+                const int bk = u + 2 * MT - 1 - l;
+                for (int x = cnt[bk]; x < cnt[bk + 1]; x++) {
+                    const T t = s_t[x];
+                    T w;
+                    if (win.mode == NFFTB200_POLYNOMIAL) {
+                        constexpr int deg = L + 1;
+                        w = pp.c[l * deg + deg - 1];
+#pragma unroll
+                        for (int r = deg - 2; r >= 0; r--) w = tfma(w, t, pp.c[l * deg + r]);
+                    } else if (win.mode == NFFTB200_LINEAR) {
+                        const T idx = mul_rn(t, (T)win.lin_scale);
+                        const int ii = (int)idx;
+                        const T alpha = sub_rn(idx, (T)ii);
+                        int a1 = ii - l * win.lin_scale, a2 = a1 + 1;
+                        a1 = a1 < 0 ? -a1 : a1; a2 = a2 < 0 ? -a2 : a2;
+                        const T v1 = win.lin[a1], v2 = win.lin[a2];
+                        w = add_rn(v1, mul_rn(alpha, sub_rn(v2, v1)));
+                    } else {
+                        w = kb_exact<T>(sub_rn(t, (T)l), MT, win.b);
+                    }
+                    if constexpr (CPLX) { ax = tfma(w, s_v[x].x, ax); ay = tfma(w, s_v[x].y, ay); }
+                    else ax = tfma(w, s_v[x], ax);
+                }
+            }
+        }
+        if constexpr (CPLX) g[t0 + u] = make_c<T>(ax, ay); else g[t0 + u] = ax;
+    }
+}
+
+template <typename T, int MT, bool CPLX>
+__global__ void __launch_bounds__(256)
+k_interp_1d(const void* __restrict__ g_, void* __restrict__ fhat_, const T* __restrict__ xs,
+            const int32_t* __restrict__ perm, long long i_lo, long long i_hi, long long M, GeomDev geo,
+            WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp, int B)
+{
+    using C = typename Cplx<T>::type;
+    using V = typename std::conditional<CPLX, C, T>::type;
+    constexpr int L = 2 * MT;
+    const int Nt = geo.Nt[0];
+    for (long long i = i_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < i_hi; i += (long long)gridDim.x * blockDim.x) {
+        T ks;
+        const int c = node_cell<T>(xs[i], Nt, ks);
+        T w[L];
+        eval_taps<T, MT>(win, pp, ks, c, w);
+        int cell = c - MT + 1;
+        cell = cell < 0 ? cell + Nt : cell;
+        const long long j = perm[i];
+        for (int b = 0; b < B; b++) {
+            const V* g = reinterpret_cast<const V*>(g_) + (long long)b * geo.gsz;
+            T ax = 0, ay = 0;
+            int cc = cell;
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                if constexpr (CPLX) { const C v = g[cc]; ax = tfma(w[l], v.x, ax); ay = tfma(w[l], v.y, ay); }
+                else ax = tfma(w[l], g[cc], ax);
+                cc = (cc + 1 == Nt) ? 0 : cc + 1;
+            }
+            if constexpr (CPLX) reinterpret_cast<C*>(fhat_)[(long long)b * M + j] = make_c<T>(ax, ay);
+            else reinterpret_cast<T*>(fhat_)[(long long)b * M + j] = ax;
+        }
+    }
+}
+
+template <typename T, int MT, bool CPLX>
+int spread1d_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi, int cap)
+{
+    using C = typename Cplx<T>::type;
+    const int W = NFFTB_G1D + 2 * MT;
+    const int S = (int)((p->bs[0] + NFFTB_G1D - 1) / NFFTB_G1D);
+    const size_t vsz = CPLX ? sizeof(C) : sizeof(T);
+    const size_t smem = ((sizeof(int) * (size_t)(2 * W + 1) + 15) & ~(size_t)15) + (sizeof(T) + vsz + sizeof(int)) * (size_t)cap + 16;
+    auto kern = k_spread_1d<T, MT, CPLX>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(p->ntiles * S), B);
+    kern<<<grid, O1_THREADS, smem, p->stream>>>(fhat, g, (const T*)p->d_xs, p->d_perm, p->d_tile_start, t_lo, t_hi,
+                                               p->M, make_geom<T>(p), make_win<T>(p), make_poly_param<T, MT>(p), cap, S);
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
+}  // namespace
+
+// returns -1 when the 1-D kernels do not apply (then the generic kernels run)
+template <typename T>
+static int spread1d_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_complex, int t_lo, int t_hi)
+{
+    if (p->m < 2 || p->m > 6 || p->bs[0] < p->m || p->Nt[0] < p->bs[0] + 2 * p->m) return -1;
+    // every tile core must be at least m long so that only the immediate neighbours reach into a tile
+    if (p->Nt[0] - (p->nb[0] - 1) * p->bs[0] < p->m) return -1;
+    // shared-memory capacity: the largest per-tile neighbourhood, counted at nodes! (k_count_neigh_1d)
+    const int64_t worst = p->max_neigh_1d;
+    const size_t vsz = (is_complex ? 2 : 1) * sizeof(T);
+    const int64_t W = NFFTB_G1D + 2 * p->m;
+    const int64_t cap_max = ((int64_t)200 * 1024 - (int64_t)sizeof(int) * (2 * W + 4)) / (int64_t)(sizeof(T) + vsz + sizeof(int)) - 4;
+    if (worst > cap_max) return -1;
+    const int cap = (int)std::max<int64_t>(worst, 32);
+#define GO(MM)                                                                                         \
+    case MM:                                                                                           \
+        return is_complex ? spread1d_launch<T, MM, true>(p, fhat, g, B, t_lo, t_hi, cap)               \
+                          : spread1d_launch<T, MM, false>(p, fhat, g, B, t_lo, t_hi, cap);
+    switch (p->m) { GO(2) GO(3) GO(4) GO(5) GO(6) default: return -1; }
+#undef GO
+}
+
+template <typename T>
+static int interp1d_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_complex, long long i_lo, long long i_hi)
+{
+    if (p->m < 2 || p->m > 6 || p->Nt[0] < 2 * p->m) return -1;
+    const long long n = i_hi - i_lo;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+#define GO(MM)                                                                                                   \
+    case MM:                                                                                                     \
+        if (is_complex) k_interp_1d<T, MM, true><<<blocks, 256, 0, p->stream>>>(g, fhat, (const T*)p->d_xs, p->d_perm, i_lo, i_hi, p->M, make_geom<T>(p), make_win<T>(p), make_poly_param<T, MM>(p), B); \
+        else k_interp_1d<T, MM, false><<<blocks, 256, 0, p->stream>>>(g, fhat, (const T*)p->d_xs, p->d_perm, i_lo, i_hi, p->M, make_geom<T>(p), make_win<T>(p), make_poly_param<T, MM>(p), B); \
+        break;
+    switch (p->m) { GO(2) GO(3) GO(4) GO(5) GO(6) default: return -1; }
+#undef GO
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
+int nfftb_spread_1d(nfftb200_plan* p, const void* fhat, void* g, int B, int is_complex, int t_lo, int t_hi)
+{
+    return p->dtype == NFFTB200_F32 ? spread1d_impl<float>(p, fhat, g, B, is_complex, t_lo, t_hi)
+                                    : spread1d_impl<double>(p, fhat, g, B, is_complex, t_lo, t_hi);
+}
+int nfftb_interp_1d(nfftb200_plan* p, const void* g, void* fhat, int B, int is_complex, long long i_lo, long long i_hi)
+{
+    return p->dtype == NFFTB200_F32 ? interp1d_impl<float>(p, g, fhat, B, is_complex, i_lo, i_hi)
+                                    : interp1d_impl<double>(p, g, fhat, B, is_complex, i_lo, i_hi);
+}

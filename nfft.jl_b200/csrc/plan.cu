@@ -307,7 +307,7 @@ int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
         p->cap_nodes = M;
     }
     const int64_t nCTA = (M + 4095) / 4096;
-    ST_TRY(ensure(p, (void**)&p->d_hist, &p->cap_hist, std::max<int64_t>(1, nCTA) * 256 * 4));
+    ST_TRY(ensure(p, (void**)&p->d_hist, &p->cap_hist, (std::max<int64_t>(1, nCTA) * 256 + std::max<int64_t>(1, nCTA) / 16 + 64) * 4));
     p->M = M;
     const void* dk = nullptr;
     ST_TRY(stage_in(p, k, M * p->D * (int64_t)p->esz(), where, &p->d_stage_k, &p->cap_stage_k, &dk));

@@ -59,25 +59,73 @@ __global__ void k_radix_hist(const uint32_t* __restrict__ keys, long long M, int
     hist[(long long)threadIdx.x * nCTA + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of n uint32 in place, one CTA of 1024 threads (plan-time only)
-__global__ void k_exclusive_scan(uint32_t* __restrict__ a, long long n)
+// exclusive scan of n uint32 in place: (A) per-CTA scan of 4096-element chunks + chunk sums, (B) scan of the
+// chunk sums by one CTA, (C) add the chunk offsets.  Coalesced accesses throughout.
+constexpr int SCAN_CHUNK = 4096;     // 1024 threads x 4
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* warp_sums, uint32_t& total)
 {
-    __shared__ uint32_t part[1024];
-    const int t = threadIdx.x;
-    const long long seg = (n + 1023) / 1024;
-    const long long lo = min((long long)t * seg, n), hi = min(lo + seg, n);
-    uint32_t s = 0;
-    for (long long i = lo; i < hi; i++) s += a[i];
-    part[t] = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        uint32_t v = (t >= off) ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    total = warp_sums[31];
+    const uint32_t base = warp == 0 ? 0u : warp_sums[warp - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_chunks(uint32_t* __restrict__ a, long long n, uint32_t* __restrict__ sums)
+{
+    __shared__ uint32_t ws[32];
+    const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (base + k < n) ? a[base + k] : 0u;
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan_1024(mine, ws, total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < n) a[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ sums, int n)
+{
+    __shared__ uint32_t ws[32];
+    uint32_t carry = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n ? sums[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan_1024(v, ws, total);
+        if (i < n) sums[i] = carry + ex;
+        carry += total;
         __syncthreads();
     }
-    uint32_t run = part[t] - s;
-    for (long long i = lo; i < hi; i++) { uint32_t v = a[i]; a[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t* __restrict__ a, long long n, const uint32_t* __restrict__ sums)
+{
+    const uint32_t off = sums[blockIdx.x];
+    const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + k < n) a[base + k] += off;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -164,6 +212,36 @@ __global__ void k_gather_nodes(const T* __restrict__ k, const int32_t* __restric
     xs[q] = shift_node<T>(k[(long long)perm[i] * D + d]);
 }
 
+// 1-D only: the output-stationary spreader works on sub-blocks of NFFTB_G1D cells inside a tile; the number of
+// nodes one sub-block must bucket = its own nodes + the nodes within m cells on either side.  The maximum over
+// all sub-blocks sizes the kernel's shared-memory buffers.
+template <typename T>
+__global__ void k_count_neigh_1d(const T* __restrict__ xs, long long M, GeomDev g, int m, int S, int* __restrict__ cnt)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    T ks;
+    const int c = node_cell<T>(xs[i], g.Nt[0], ks);
+    const int bs = g.bs[0], nb = g.nb[0], Nt = g.Nt[0];
+    auto block_of = [&](int cell) {                  // sub-block index of a (wrapped) cell
+        cell = cell < 0 ? cell + Nt : (cell >= Nt ? cell - Nt : cell);
+        const int t = cell / bs;
+        return t * S + (cell - t * bs) / NFFTB_G1D;
+    };
+    const int b0 = block_of(c);
+    atomicAdd(&cnt[b0], 1);
+    const int bl = block_of(c - (m - 1)), bh = block_of(c + m);   // blocks whose cells this node's taps reach
+    if (bl != b0) atomicAdd(&cnt[bl], 1);
+    if (bh != b0 && bh != bl) atomicAdd(&cnt[bh], 1);
+    (void)nb;
+}
+__global__ void k_max_int(const int* __restrict__ a, long long n, int* __restrict__ out)
+{
+    int mx = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) mx = max(mx, a[i]);
+    atomicMax(out, mx);
+}
+
 template <typename T> int sort_impl(nfftb200_plan* p, const void* d_k)
 {
     const long long M = p->M;
@@ -192,7 +270,15 @@ template <typename T> int sort_impl(nfftb200_plan* p, const void* d_k)
         for (int ps = 0; ps < passes; ps++) {
             const int shift = 8 * ps;
             k_radix_hist<<<nCTA, SORT_THREADS, 0, s>>>(p->d_keys[cur], M, shift, p->d_hist, nCTA);
-            k_exclusive_scan<<<1, 1024, 0, s>>>(p->d_hist, 256ll * nCTA);
+            {
+                const long long hn = 256ll * nCTA;
+                const int nchunks = (int)((hn + SCAN_CHUNK - 1) / SCAN_CHUNK);
+                uint32_t* sums = p->d_hist + hn;                     // scratch right after the histogram
+                k_scan_chunks<<<nchunks, 1024, 0, s>>>(p->d_hist, hn, sums);
+                k_scan_sums<<<1, 1024, 0, s>>>(sums, nchunks);
+                k_scan_add<<<nchunks, 1024, 0, s>>>(p->d_hist, hn, sums);
+                p->launches += 2;
+            }
             k_radix_scatter<<<nCTA, SORT_THREADS, 0, s>>>(
                 p->d_keys[cur], ps == 0 ? nullptr : p->d_vals[cur], p->d_keys[cur ^ 1],
                 p->d_vals[cur ^ 1], M, shift, p->d_hist, nCTA);
@@ -209,6 +295,22 @@ template <typename T> int sort_impl(nfftb200_plan* p, const void* d_k)
         k_gather_nodes<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const T*)d_k, p->d_perm, M,
                                                                     p->D, (T*)p->d_xs);
         p->launches++;
+    }
+    p->max_neigh_1d = 0;
+    if (p->D == 1 && M > 0) {
+        int* d_cnt = nullptr;
+        const int S = (int)((p->bs[0] + NFFTB_G1D - 1) / NFFTB_G1D);
+        const long long nblk = p->ntiles * S;
+        CUDA_TRY(p, cudaMalloc(&d_cnt, sizeof(int) * (size_t)(nblk + 1)));
+        CUDA_TRY(p, cudaMemsetAsync(d_cnt, 0, sizeof(int) * (size_t)(nblk + 1), s));
+        k_count_neigh_1d<T><<<(unsigned)((M + 255) / 256), 256, 0, s>>>((const T*)p->d_xs, M, g, p->m, S, d_cnt);
+        k_max_int<<<64, 256, 0, s>>>(d_cnt, nblk, d_cnt + nblk);
+        int mx = 0;
+        CUDA_TRY(p, cudaMemcpyAsync(&mx, d_cnt + nblk, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(p, cudaStreamSynchronize(s));
+        cudaFree(d_cnt);
+        p->max_neigh_1d = mx;
+        p->launches += 2;
     }
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;

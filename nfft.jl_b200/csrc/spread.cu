@@ -508,6 +508,14 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
                 long long i_lo, long long i_hi)
 {
     const size_t cell = is_complex ? 2 * sizeof(T) : sizeof(T);
+    if (p->kernel_mode != 1 && p->D == 1) {        // output-stationary 1-D spreader: writes every cell, no memset
+        if (p->timing) { cudaEventRecord(p->evk[0], p->stream); cudaEventRecord(p->evk[1], p->stream); }
+        const int r = nfftb_spread_1d(p, fhat, g, B, is_complex, t_lo, t_hi);
+        if (r >= 0) {
+            if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; }
+            return r;
+        }
+    }
     if (i_hi > i_lo && p->kernel_mode != 1 && is_complex && p->D == 3) {
         int r = -1;
         switch (p->m) {
