@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0)
+    ap.add_argument("--block-size", type=str, default="", help="override the plan tile, e.g. 16,16,16 (experiments)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -151,11 +152,12 @@ def main():
     N, M, T = w["N"], w["M"], w["T"]
     k = O.random_nodes(M, 3, T, seed=1)                     # same nodes on every rank (shared by the batch)
     kd = torch.from_numpy(np.ascontiguousarray(k.T)).cuda()
+    bsz = tuple(int(x) for x in args.block_size.split(",")) if args.block_size else None
     if world > 1:      # batched plan with ntransforms = world, one transform per rank, no data-path collective
-        p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"], ntransforms=world, shard="batch")
+        p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"], ntransforms=world, shard="batch", blockSize=bsz)
         assert p.ntransforms == 1
     else:
-        p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"])
+        p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"], blockSize=bsz)
     p.set_kernel_mode(args.kernel_mode)
     f_h = O.random_complex(N, T, 100 + rank)
     fh_h = O.random_complex(M, T, 200 + rank)

@@ -94,6 +94,12 @@ struct nfftb200_plan {
     int32_t* d_perm = nullptr;       // sorted position -> original node id
     int32_t* d_tile_start = nullptr; // ntiles + 1
     std::vector<int32_t> h_tile_start;  // host copy (tile-aligned sharding, launch ranges)
+    // work items: a tile with more than item_cap nodes is split (after the sort) into several items, each a
+    // (tile, node range) triple processed by its own CTA; d_tile_items[t]..[t+1] are tile t's items
+    int32_t* d_items = nullptr;      // 3 * nitems: tile, n_lo, n_hi
+    int32_t* d_tile_items = nullptr; // ntiles + 1
+    std::vector<int32_t> h_tile_items;
+    int64_t nitems = 0, cap_items = 0;
     int64_t cap_nodes = 0;
     int max_neigh_1d = 0;            // 1-D: max nodes a tile's output-stationary spreader must bucket
 
@@ -197,5 +203,7 @@ int nfftb_interp(nfftb200_plan* p, const void* d_g, void* d_fhat, int B, int is_
                  int64_t t_lo, int64_t t_hi);                                   // interp.cu
 int nfftb_build_tables(nfftb200_plan* p);
 size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs);                // spread.cu
+int nfftb_spread_2d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi);                    // twod.cu
+int nfftb_interp_2d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi);
 int nfftb_spread_1d(nfftb200_plan* p, const void* fhat, void* g, int B, int is_complex, int t_lo, int t_hi);   // oned.cu
 int nfftb_interp_1d(nfftb200_plan* p, const void* g, void* fhat, int B, int is_complex, long long i_lo, long long i_hi);                                       // tables.cpp

@@ -20,17 +20,6 @@ __device__ __forceinline__ int wrap(int v, int n)
     return v < 0 ? v + n : v;
 }
 
-// asynchronous global -> shared copy of one complex cell (LDGSTS; no register staging, every row of the
-// tile is in flight at once)
-__device__ __forceinline__ void cp_async_cell(float2* dst, const float2* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_cell(double2* dst, const double2* src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-
 template <typename T> __device__ __forceinline__ T warp_sum(T v)
 {
 #pragma unroll
@@ -127,9 +116,9 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     T* rec_w = reinterpret_cast<T*>(res + TI_WARPS * 32);                       // [8][32][RW]
     int* rec_i = reinterpret_cast<int*>(rec_w + TI_WARPS * 32 * RW);            // [8][32][2]
 
-    const int tile_id = tile_lo + blockIdx.x;
-    const int n_lo = tile_start[tile_id], n_hi = tile_start[tile_id + 1];
-    if (n_hi == n_lo) return;
+    const int32_t* item = tile_start + 3 * (size_t)(tile_lo + blockIdx.x);     // work item (tile, node range)
+    const int tile_id = item[0];
+    const int n_lo = item[1], n_hi = item[2];
     const int tx = tile_id % geo.nb[0];
     const int ty = (tile_id / geo.nb[0]) % geo.nb[1];
     const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
@@ -314,9 +303,11 @@ int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, 
     if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
     auto kern = k_interp_row3d<T, MT>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(t_hi - t_lo, B);
+    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
+    if (item_hi == item_lo) return NFFTB200_OK;
+    dim3 grid(item_hi - item_lo, B);
     kern<<<grid, TI_THREADS, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm,
-                                               p->d_tile_start, t_lo, p->M, geo, make_win<T>(p),
+                                               p->d_items, item_lo, p->M, geo, make_win<T>(p),
                                                make_poly_param<T, MT>(p));
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
@@ -335,6 +326,10 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
     } kt(p);
     if (p->kernel_mode != 1 && p->D == 1) {
         const int r = nfftb_interp_1d(p, g, fhat, B, is_complex, i_lo, i_hi);
+        if (r >= 0) return r;
+    }
+    if (p->kernel_mode != 1 && is_complex && p->D == 2) {
+        const int r = nfftb_interp_2d(p, g, fhat, B, t_lo, t_hi);
         if (r >= 0) return r;
     }
     if (p->kernel_mode != 1 && is_complex && p->D == 3) {

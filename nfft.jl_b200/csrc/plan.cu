@@ -276,7 +276,7 @@ int nfftb200_destroy(nfftb200_plan* p)
     if (p->have_fft) cufftDestroy(p->fft);
     void* bufs[] = {p->d_hat_inv, p->d_poly, p->d_lin, p->d_grid, p->d_xs, p->d_tile_start, p->d_keys[0],
                     p->d_keys[1], p->d_vals[0], p->d_vals[1], p->d_hist, p->d_flag, p->d_stage_f,
-                    p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab, p->d_tilebuf};
+                    p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab, p->d_tilebuf, p->d_items, p->d_tile_items};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 4; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     for (int i = 0; i < 5; i++) if (p->evk[i]) cudaEventDestroy(p->evk[i]);
@@ -315,6 +315,36 @@ int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
     p->h_tile_start.resize((size_t)p->ntiles + 1);
     CUDA_TRY(p, cudaMemcpyAsync(p->h_tile_start.data(), p->d_tile_start, sizeof(int32_t) * (size_t)(p->ntiles + 1),
                                 cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    {   // work items (load balancing of crowded tiles, e.g. the k-space centre of radial trajectories)
+        const int64_t cap = p->D == 3 ? 4096 : 2048;
+        std::vector<int32_t> items;
+        p->h_tile_items.assign((size_t)p->ntiles + 1, 0);
+        for (int64_t t = 0; t < p->ntiles; t++) {
+            p->h_tile_items[(size_t)t] = (int32_t)(items.size() / 3);
+            const int64_t lo = p->h_tile_start[(size_t)t], hi = p->h_tile_start[(size_t)t + 1];
+            if (hi == lo) continue;
+            const int64_t parts = (hi - lo + cap - 1) / cap;
+            for (int64_t q = 0; q < parts; q++) {
+                items.push_back((int32_t)t);
+                items.push_back((int32_t)(lo + (hi - lo) * q / parts));
+                items.push_back((int32_t)(lo + (hi - lo) * (q + 1) / parts));
+            }
+        }
+        p->h_tile_items[(size_t)p->ntiles] = (int32_t)(items.size() / 3);
+        p->nitems = (int64_t)items.size() / 3;
+        if (!p->d_tile_items) CUDA_TRY(p, cudaMalloc((void**)&p->d_tile_items, sizeof(int32_t) * (size_t)(p->ntiles + 1)));
+        if (p->nitems > p->cap_items) {
+            if (p->d_items) cudaFree(p->d_items);
+            p->d_items = nullptr; p->cap_items = 0;
+            CUDA_TRY(p, cudaMalloc((void**)&p->d_items, sizeof(int32_t) * 3 * (size_t)p->nitems));
+            p->cap_items = p->nitems;
+        }
+        if (p->nitems > 0)
+            CUDA_TRY(p, cudaMemcpyAsync(p->d_items, items.data(), sizeof(int32_t) * items.size(), cudaMemcpyHostToDevice, p->stream));
+        CUDA_TRY(p, cudaMemcpyAsync(p->d_tile_items, p->h_tile_items.data(), sizeof(int32_t) * (size_t)(p->ntiles + 1),
+                                    cudaMemcpyHostToDevice, p->stream));
+    }
     if (p->timing) cudaEventRecord(p->ev[1], p->stream);
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     if (p->timing) { float ms = 0; cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->t[0] = ms * 1e-3; }

@@ -82,30 +82,30 @@ k_spread_generic(const void* __restrict__ fhat_, void* __restrict__ g_, const T*
 // ---------------------------------------------------------------------------------------
 // tiled 3-D spreader: warp-private padded sub-tiles, row-per-lane accumulation
 // ---------------------------------------------------------------------------------------
-constexpr int SS_WARPS = 8;
-constexpr int SS_THREADS = SS_WARPS * 32;
 constexpr int SS_CHUNK = 1024;       // nodes whose octant ids are cached per pass
 
-template <typename T, int MT> struct SubLayout {
+// NW = 8: octants 2x2x2, one CTA per SM;  NW = 4: quadrants 2x2x1 (for tiles that are half as thick), two CTAs
+// per SM so that one CTA's shared-memory-bound accumulation overlaps the other's weight/merge/flush phases.
+template <typename T, int MT, int NW> struct SubLayout {
     using RG = RowGeom<T, MT>;
     static constexpr int L = 2 * MT;
     static constexpr int RW = ((RG::NWX + L + 2 * L) + 3) & ~3;     // record: wx(shifted) | wy | wz*v
     int SX, SY, SZ, QX, QY, QZ, QN;
     __host__ __device__ SubLayout(const int* bs)
     {
-        SX = (bs[0] + 1) / 2; SY = (bs[1] + 1) / 2; SZ = (bs[2] + 1) / 2;
+        SX = (bs[0] + 1) / 2; SY = (bs[1] + 1) / 2; SZ = (NW == 8) ? (bs[2] + 1) / 2 : bs[2];
         QX = SX + L; QY = SY + L; QZ = SZ + L;
         QN = (QX * QY * QZ + 2 * RG::VPC + 1) & ~1;                 // tail pad for the widened last row
     }
     __host__ __device__ size_t bytes() const
     {
-        return sizeof(typename Cplx<T>::type) * (size_t)SS_WARPS * QN + sizeof(T) * SS_WARPS * 32 * RW +
-               sizeof(int) * SS_WARPS * 32 + sizeof(unsigned short) * SS_WARPS * 64 + SS_CHUNK;
+        return sizeof(typename Cplx<T>::type) * (size_t)NW * QN + sizeof(T) * NW * 32 * RW +
+               sizeof(int) * NW * 32 + sizeof(unsigned short) * NW * 64 + SS_CHUNK;
     }
 };
 
-template <typename T, int MT, bool SCRATCH>
-__global__ void __launch_bounds__(SS_THREADS, 1)
+template <typename T, int MT, bool SCRATCH, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1)
 k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>::type* __restrict__ g,
                typename Cplx<T>::type* __restrict__ scratch,
                const T* __restrict__ xs, const int32_t* __restrict__ perm,
@@ -114,8 +114,9 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
 {
     using C = typename Cplx<T>::type;
     using RG = RowGeom<T, MT>;
-    using SL = SubLayout<T, MT>;
+    using SL = SubLayout<T, MT, NW>;
     constexpr int L = 2 * MT, VPC = RG::VPC, NV = RG::NV, NWX = RG::NWX, RW = SL::RW;
+    constexpr int SS_WARPS = NW, SS_THREADS = NW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SL lay(geo.bs);
     const int QX = lay.QX, QY = lay.QY, QN = lay.QN;
@@ -125,9 +126,10 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     unsigned short* list = reinterpret_cast<unsigned short*>(rec_b + SS_WARPS * 32);   // [8][64]
     unsigned char* oct = reinterpret_cast<unsigned char*>(list + SS_WARPS * 64);      // [SS_CHUNK]
 
-    const int tile_id = tile_lo + blockIdx.x;
-    const int n_lo = tile_start[tile_id], n_hi = tile_start[tile_id + 1];
-    if (n_hi == n_lo) return;                                                   // grid is pre-zeroed
+    // blockIdx.x walks work items (tile, node range); tile_start is the item table here
+    const int32_t* item = tile_start + 3 * (size_t)(tile_lo + blockIdx.x);
+    const int tile_id = item[0];
+    const int n_lo = item[1], n_hi = item[2];
     const int tx = tile_id % geo.nb[0];
     const int ty = (tile_id / geo.nb[0]) % geo.nb[1];
     const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
@@ -271,7 +273,7 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
             const int l0 = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks) - cx0;
             const int l1 = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks) - cy0;
             const int l2 = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks) - cz0;
-            oct[q] = (unsigned char)((l0 >= lay.SX) + 2 * (l1 >= lay.SY) + 4 * (l2 >= lay.SZ));
+            oct[q] = (unsigned char)((l0 >= lay.SX) + 2 * (l1 >= lay.SY) + ((NW == 8) ? 4 * (l2 >= lay.SZ) : 0));
         }
         __syncthreads();
         int cnt = 0;
@@ -307,7 +309,7 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     {
         const int SX = lay.SX, SY = lay.SY, SZ = lay.SZ, QZ = lay.QZ;
         const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
-        {   // z
+        if (NW == 8) {   // z
             const int blk = L * QY * QX;
             for (int q = threadIdx.x; q < 4 * blk; q += SS_THREADS) {
                 const int col = q / blk, r = q - col * blk;
@@ -316,14 +318,14 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                 C c = *d; c.x += a.x; c.y += a.y; *d = c;
             }
         }
-        __syncthreads();
-        {   // y: live planes of octant oz: oz==0 -> [0,SZ), oz==1 -> [0,QZ)
-            const int blk = L * QX, npl = SZ + QZ;
+        if (NW == 8) __syncthreads();
+        {   // y: live planes of octant oz: oz==0 -> [0,SZ), oz==1 -> [0,QZ)   (NW == 4: a single z layer, all planes live)
+            const int blk = L * QX, npl = (NW == 8) ? SZ + QZ : QZ;
             const unsigned inv = fastdiv_inv(blk);
             for (int q = threadIdx.x; q < 2 * npl * blk; q += SS_THREADS) {
                 const int pb = (int)fastdiv(q, inv), r = q - pb * blk;
                 const int ox_ = pb >= npl, pl = pb - ox_ * npl;
-                const int oz_ = pl >= SZ, zz = pl - oz_ * SZ;
+                const int oz_ = (NW == 8) ? (pl >= SZ) : 0, zz = pl - oz_ * SZ;
                 const int o = ox_ + 4 * oz_;
                 const C a = sub[o * QN + (zz * QY + SY) * QX + r];
                 C* d = sub + (o + 2) * QN + zz * QY * QX + r;
@@ -336,7 +338,7 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
             for (int q = threadIdx.x; q < PY * PZ * L; q += SS_THREADS) {
                 const int row = (int)fastdiv(q, invL), xx = q - row * L;
                 const int z = (int)fastdiv(row, invPY), y = row - z * PY;
-                const int oy_ = y >= SY, oz_ = z >= SZ;
+                const int oy_ = y >= SY, oz_ = (NW == 8) ? (z >= SZ) : 0;
                 const int o = 2 * oy_ + 4 * oz_;
                 const int ro = ((z - oz_ * SZ) * QY + (y - oy_ * SY)) * QX;
                 const C a = sub[o * QN + ro + SX + xx];
@@ -355,11 +357,11 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
         // every warp walks all z-planes and owns rows y = warp + 8k of each (k unrolled => independent
         // address chains in flight; with one CTA per SM the ILP has to come from inside the warp)
         for (int z = 0; z < PZ; z++) {
-            const int oz_ = z >= SZ;
+            const int oz_ = (NW == 8) ? (z >= SZ) : 0;
             const C* pz_ = sub + 4 * oz_ * QN + (z - oz_ * SZ) * QY * QX;
             const unsigned gz = (unsigned)wrapc(cz0 - MT + z, geo.Nt[2], fw) * geo.Nt[1];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < 32 / SS_WARPS; k++) {
                 const int y = warp + SS_WARPS * k;
                 if (y < PY) {
                     const int oy_ = y >= SY;
@@ -386,7 +388,7 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
 template <typename T, int MT>
 __global__ void __launch_bounds__(256)
 k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cplx<T>::type* __restrict__ g,
-                 const int32_t* __restrict__ tile_start, int tile_lo, int tile_hi, GeomDev geo)
+                 const int32_t* __restrict__ tile_start, int tile_lo, int tile_hi, int item_lo, int item_hi, GeomDev geo)
 {
     using C = typename Cplx<T>::type;
     constexpr int L = 2 * MT, VPC = 16 / (int)sizeof(C);
@@ -395,7 +397,7 @@ k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cp
     const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * VPC;
     const int u1 = blockIdx.y, u2 = blockIdx.z % geo.Nt[2], b = blockIdx.z / geo.Nt[2];
     if (u0 >= geo.Nt[0]) return;
-    scratch += (size_t)b * (tile_hi - tile_lo) * PN;
+    scratch += (size_t)b * (item_hi - item_lo) * PN;
     // per dimension: the (tile, padded coordinate) pairs that cover cell u; packed as tile*stride + p offsets
     // so that the inner loops are pure adds.  Offsets are in cells of the scratch buffer.
     auto cover = [&](int u, int d, unsigned inv, size_t tstride, size_t pstride, size_t (&off)[3], int (&tid)[3], int tmul) -> int {
@@ -432,9 +434,10 @@ k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cp
                 for (int ix = 0; ix < nx; ix++) {
                     const int tile = tyz + tx[ix];
                     if (tile < tile_lo || tile >= tile_hi) continue;
-                    if (tile_start[tile + 1] == tile_start[tile]) continue;        // empty tile: never written
-                    const C c = scratch[(size_t)(tile - tile_lo) * PN + oyz + ox[ix]];
-                    acc[k].x += c.x; acc[k].y += c.y;
+                    for (int it = tile_start[tile]; it < tile_start[tile + 1]; it++) {   // tile_start = d_tile_items here
+                        const C c = scratch[(size_t)(it - item_lo) * PN + oyz + ox[ix]];
+                        acc[k].x += c.x; acc[k].y += c.y;
+                    }
                 }
             }
     }
@@ -445,12 +448,13 @@ k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cp
 
 // returns -1 if the tiled kernel does not apply, else a status; *wrote_all = true if every grid cell was
 // written by the gather pass (no memset needed)
-template <typename T, int MT>
-int launch_tile3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi)
+template <typename T, int MT, int NW>
+int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi)
 {
     using C = typename Cplx<T>::type;
+    constexpr int SS_THREADS = NW * 32;
     GeomDev geo = make_geom<T>(p);
-    SubLayout<T, MT> lay(geo.bs);
+    SubLayout<T, MT, NW> lay(geo.bs);
     const size_t smem = lay.bytes();
     if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
     bool use_scratch = p->kernel_mode != 2;
@@ -460,9 +464,11 @@ int launch_tile3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, 
     }
     const size_t PN = (size_t)(geo.bs[0] + 2 * MT) * (geo.bs[1] + 2 * MT) * (geo.bs[2] + 2 * MT);
     const cudaStream_t st = p->stream;
-    dim3 grid(t_hi - t_lo, B);
+    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
+    if (item_hi == item_lo) use_scratch = false;
+    dim3 grid(item_hi - item_lo, B);
     if (use_scratch) {
-        const int64_t need = (int64_t)(sizeof(C) * PN * (size_t)(t_hi - t_lo) * B);
+        const int64_t need = (int64_t)(sizeof(C) * PN * (size_t)(item_hi - item_lo) * B);
         if (need > p->cap_tilebuf) {
             if (p->d_tilebuf) cudaFree(p->d_tilebuf);
             p->d_tilebuf = nullptr; p->cap_tilebuf = 0;
@@ -478,29 +484,41 @@ int launch_tile3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, 
     if (use_scratch) {
         if (p->timing) cudaEventRecord(p->evk[0], st);
         KT kt(p);
-        auto kern = k_spread_sub3d<T, MT, true>;
+        auto kern = k_spread_sub3d<T, MT, true, NW>;
         CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SS_THREADS, smem, st>>>((const C*)fhat, (C*)g, (C*)p->d_tilebuf, (const T*)p->d_xs, p->d_perm,
-                                            p->d_tile_start, t_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
+                                            p->d_items, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
         constexpr int VPC = 16 / (int)sizeof(C);
         const int units = (geo.Nt[0] + VPC - 1) / VPC;
         int bx = 32;
         while (bx < 256 && bx < units) bx <<= 1;
         dim3 gg((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);
-        k_gather_tiles3d<T, MT><<<gg, bx, 0, st>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_start, t_lo, t_hi, geo);
+        k_gather_tiles3d<T, MT><<<gg, bx, 0, st>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo);
         p->launches += 2;
     } else {
         if (p->timing) cudaEventRecord(p->evk[0], st);
         CUDA_TRY(p, cudaMemsetAsync(g, 0, sizeof(C) * (size_t)p->gsz * B, st));
         KT kt(p);
-        auto kern = k_spread_sub3d<T, MT, false>;
+        auto kern = k_spread_sub3d<T, MT, false, NW>;
         CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, SS_THREADS, smem, st>>>((const C*)fhat, (C*)g, nullptr, (const T*)p->d_xs, p->d_perm,
-                                            p->d_tile_start, t_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
+        if (item_hi > item_lo)
+            kern<<<grid, SS_THREADS, smem, st>>>((const C*)fhat, (C*)g, nullptr, (const T*)p->d_xs, p->d_perm,
+                                                p->d_items, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
         p->launches += 2;
     }
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;
+}
+
+// thin tiles (bs_z <= 8) run with 4 warps / 2 CTAs per SM, thick ones with 8 warps / 1 CTA per SM
+template <typename T, int MT>
+int launch_tile3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi)
+{
+    if (p->bs[2] <= 8) {
+        const int r = launch_tile3d_nw<T, MT, 4>(p, fhat, g, B, t_lo, t_hi);
+        if (r >= 0) return r;
+    }
+    return launch_tile3d_nw<T, MT, 8>(p, fhat, g, B, t_lo, t_hi);
 }
 
 template <typename T>
@@ -511,6 +529,14 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
     if (p->kernel_mode != 1 && p->D == 1) {        // output-stationary 1-D spreader: writes every cell, no memset
         if (p->timing) { cudaEventRecord(p->evk[0], p->stream); cudaEventRecord(p->evk[1], p->stream); }
         const int r = nfftb_spread_1d(p, fhat, g, B, is_complex, t_lo, t_hi);
+        if (r >= 0) {
+            if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; }
+            return r;
+        }
+    }
+    if (i_hi > i_lo && p->kernel_mode != 1 && is_complex && p->D == 2) {
+        if (p->timing) { cudaEventRecord(p->evk[0], p->stream); cudaEventRecord(p->evk[1], p->stream); }
+        const int r = nfftb_spread_2d(p, fhat, g, B, t_lo, t_hi);
         if (r >= 0) {
             if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; }
             return r;
@@ -557,8 +583,10 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
 size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs)
 {
     int b[3] = {(int)bs[0], (int)bs[1], (int)bs[2]};
-#define CASE_M(MM)                                                                         \
-    case MM: return dtype == NFFTB200_F32 ? SubLayout<float, MM>(b).bytes() : SubLayout<double, MM>(b).bytes();
+#define CASE_M(MM)                                                                                        \
+    case MM:                                                                                              \
+        if (b[2] <= 8) return dtype == NFFTB200_F32 ? SubLayout<float, MM, 4>(b).bytes() : SubLayout<double, MM, 4>(b).bytes(); \
+        return dtype == NFFTB200_F32 ? SubLayout<float, MM, 8>(b).bytes() : SubLayout<double, MM, 8>(b).bytes();
     switch (m) {
         CASE_M(2) CASE_M(3) CASE_M(4) CASE_M(5) CASE_M(6)
         default: return 0;

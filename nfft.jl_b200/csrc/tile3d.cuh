@@ -98,6 +98,17 @@ __device__ __forceinline__ int wrapc(int v, int n, bool fast)
 __device__ __forceinline__ unsigned fastdiv(unsigned row, unsigned inv) { return __umulhi(row, inv); }
 __device__ __forceinline__ unsigned fastdiv_inv(unsigned d) { return (unsigned)((0x100000000ull + d - 1) / d); }
 
+// asynchronous global -> shared copy of one complex cell (LDGSTS; no register staging, every row of the
+// tile is in flight at once)
+__device__ __forceinline__ void cp_async_cell(float2* dst, const float2* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_cell(double2* dst, const double2* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 // 16-byte shared-memory unit <-> registers
 template <typename T> struct Unit;
 template <> struct Unit<float> {

@@ -272,3 +272,53 @@ def test_device_buffers_and_stage_ops(nb):
     nb.mul_(fd, p.adjoint(), out, timing=ts)
     assert ts.conv_adjoint > 0 and ts.fft_adjoint > 0 and ts.deconv_adjoint > 0
     assert p.launch_count() > 0
+
+
+@pytest.mark.parametrize("N,m,T", [((96, 80), 4, np.float64), ((96, 80), 4, np.float32), ((128, 128), 3, np.float32),
+                                   ((100, 72), 5, np.float64), ((256, 256), 4, np.float64), ((64, 96), 2, np.float32)])
+@pytest.mark.parametrize("pre", [O.POLYNOMIAL, O.LINEAR])
+def test_tiled_2d_kernels(nb, N, m, T, pre):
+    """grids large enough that the tiled 2-D kernels (twod.cu) run instead of the generic fallback"""
+    M = 30011
+    k = O.random_nodes(M, 2, T, seed=12)
+    k[:3] = 0.5; k[3:6] = -0.5; k[6] = 0.0
+    p = nb.plan_nfft(k.T, N, m=m, σ=2.0, precompute=nb.PrecomputeFlags(pre))
+    po = O.OraclePlan(k, N, m=m, sigma=2.0, precompute=pre, blockSize=p.params.blockSize)
+    fHat = O.random_complex(M, T, 2)
+    f = O.random_complex(N, T, 3)
+    assert rel(p.adjoint() * fHat, po.adjoint(fHat)) < TOL[T]
+    assert rel(p * f, po.forward(f)) < TOL[T]
+    p.set_kernel_mode(1)                                     # and the generic kernels agree with the tiled ones
+    assert rel(p.adjoint() * fHat, po.adjoint(fHat)) < TOL[T]
+
+
+def test_radial_batched_2d(nb):
+    """C3-like: radial trajectory (all spokes cross the centre tile), ntransforms = 4, density-weighted adjoint"""
+    T = np.float32
+    N = (128, 128)
+    k = O.radial_nodes(96, 256, T)
+    M, B = k.shape[0], 4
+    w = np.maximum(np.abs(np.tile((np.arange(256) - 128) / 256, 96)), 1 / 512).astype(T)
+    p = nb.plan_nfft(k.T, N, m=4, σ=2.0, ntransforms=B)
+    po = O.OraclePlan(k, N, m=4, sigma=2.0, blockSize=p.params.blockSize)
+    fh = O.random_complex((M, B), T, 5) * w[:, None]
+    f = O.random_complex(N + (B,), T, 6)
+    adj = p.adjoint() * fh
+    out = p * f
+    for b in range(B):
+        assert rel(adj[..., b], po.adjoint(np.ascontiguousarray(fh[:, b]))) < 1e-5
+        assert rel(out[:, b], po.forward(np.asfortranarray(f[..., b]))) < 1e-5
+
+
+@pytest.mark.parametrize("N,T", [((1 << 16,), np.float64), ((5000,), np.float32), ((3000,), np.float64)])
+def test_tiled_1d_kernels(nb, N, T):
+    """dense 1-D node sets (several nodes per cell) through the output-stationary spreader (oned.cu)"""
+    M = 8 * N[0] + 13
+    k = O.random_nodes(M, 1, T, seed=8)
+    k[:4, 0] = [0.5, -0.5, 0.0, -1e-9]
+    p = nb.plan_nfft(k.T, N, m=4, σ=2.0)
+    po = O.OraclePlan(k, N, m=4, sigma=2.0, blockSize=p.params.blockSize)
+    fHat = O.random_complex(M, T, 2)
+    f = O.random_complex(N, T, 3)
+    assert rel(p.adjoint() * fHat, po.adjoint(fHat)) < TOL[T]
+    assert rel(p * f, po.forward(f)) < TOL[T]
