@@ -43,6 +43,7 @@ struct GeomDev {
     int N[NFFTB_MAX_D];       // image size (padded with 1)
     int bs[NFFTB_MAX_D];      // tile size (padded with 1)
     int nb[NFFTB_MAX_D];      // tiles per dim (padded with 1)
+    unsigned inv_bs[NFFTB_MAX_D];   // ceil(2^32 / bs[d]) for division-free u / bs[d]
     long long gsz;            // prod(Nt)
     long long fsz;            // prod(N)
 };
@@ -173,6 +174,7 @@ template <typename T> inline GeomDev make_geom(const nfftb200_plan* p)
     g.D = p->D;
     for (int d = 0; d < NFFTB_MAX_D; d++) {
         g.Nt[d] = (int)p->Nt[d]; g.N[d] = (int)p->N[d]; g.bs[d] = (int)p->bs[d]; g.nb[d] = (int)p->nb[d];
+        g.inv_bs[d] = (unsigned)((0x100000000ull + (unsigned long long)p->bs[d] - 1) / (unsigned long long)p->bs[d]);
     }
     g.gsz = p->gsz; g.fsz = p->fsz;
     return g;

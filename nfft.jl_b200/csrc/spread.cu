@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "window.cuh"
 #include "tile3d.cuh"
+#include "gather.cuh"
 
 namespace {
 
@@ -382,68 +383,71 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
 }
 
 // addBlock! without the lock (/root/reference/src/convolution.jl:371-443): every grid cell sums, in a fixed
-// order, the <= 8 padded tiles that cover it and is written exactly once (so no memset of g either).
-// Preconditions checked on the host: every tile core is at least m cells long in every dimension.
-// One thread per 16-byte unit of the grid; (u1,u2) are block-uniform.
+// order, the <= 8 padded tiles (work items) that cover it and is written exactly once (so no memset of g either).
+// Preconditions checked on the host: every tile core is at least m cells long in every dimension, bs[0] even.
+// One CTA per (u1,u2) row segment: the y/z candidates are CTA-uniform, one thread handles two adjacent x cells.
 template <typename T, int MT>
 __global__ void __launch_bounds__(256)
 k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cplx<T>::type* __restrict__ g,
-                 const int32_t* __restrict__ tile_start, int tile_lo, int tile_hi, int item_lo, int item_hi, GeomDev geo)
+                 const int32_t* __restrict__ tile_items, int tile_lo, int tile_hi, int item_lo, int item_hi, GeomDev geo)
 {
     using C = typename Cplx<T>::type;
-    constexpr int L = 2 * MT, VPC = 16 / (int)sizeof(C);
+    constexpr int L = 2 * MT;
     const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
-    const size_t PN = (size_t)PX * PY * PZ;
-    const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * VPC;
+    const unsigned PN = (unsigned)PX * PY * PZ;
+    const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const int u1 = blockIdx.y, u2 = blockIdx.z % geo.Nt[2], b = blockIdx.z / geo.Nt[2];
     if (u0 >= geo.Nt[0]) return;
-    scratch += (size_t)b * (item_hi - item_lo) * PN;
-    // per dimension: the (tile, padded coordinate) pairs that cover cell u; packed as tile*stride + p offsets
-    // so that the inner loops are pure adds.  Offsets are in cells of the scratch buffer.
-    auto cover = [&](int u, int d, unsigned inv, size_t tstride, size_t pstride, size_t (&off)[3], int (&tid)[3], int tmul) -> int {
+    scratch += (size_t)b * (size_t)(item_hi - item_lo) * PN;
+    // candidates along one dimension: (tile coordinate * tmul, padded offset * pmul)
+    auto cover = [&](int u, int d, int tmul, int pmul, int (&tt)[3], int (&po)[3]) -> int {
         const int bs = geo.bs[d], nb = geo.nb[d], Nt = geo.Nt[d];
-        const int t = (int)fastdiv((unsigned)u, inv), l = u - t * bs;
+        const int t = (int)fastdiv((unsigned)u, geo.inv_bs[d]), l = u - t * bs;
         const int len = (t == nb - 1) ? Nt - t * bs : bs;
         int n = 0;
-        tid[n] = t * tmul; off[n] = (size_t)(l + MT) * pstride; n++;
-        if (l < MT) {                                   // high halo of the previous tile
+        tt[n] = t * tmul; po[n] = (l + MT) * pmul; n++;
+        if (l < MT) {
             const int tp = t == 0 ? nb - 1 : t - 1;
             const int lenp = (tp == nb - 1) ? Nt - tp * bs : bs;
-            tid[n] = tp * tmul; off[n] = (size_t)(l + MT + lenp) * pstride; n++;
+            tt[n] = tp * tmul; po[n] = (l + MT + lenp) * pmul; n++;
         }
-        if (l >= len - MT) {                            // low halo of the next tile
-            tid[n] = (t == nb - 1 ? 0 : t + 1) * tmul; off[n] = (size_t)(l + MT - len) * pstride; n++;
-        }
+        if (l >= len - MT) { tt[n] = (t == nb - 1 ? 0 : t + 1) * tmul; po[n] = (l + MT - len) * pmul; n++; }
         return n;
     };
-    size_t oy[3], oz[3], ox[3];
-    int ty[3], tz[3], tx[3];
-    const int ny = cover(u1, 1, fastdiv_inv(geo.bs[1]), 0, (size_t)PX, oy, ty, geo.nb[0]);
-    const int nz = cover(u2, 2, fastdiv_inv(geo.bs[2]), 0, (size_t)PX * PY, oz, tz, geo.nb[0] * geo.nb[1]);
-    const unsigned invx = fastdiv_inv(geo.bs[0]);
-    C acc[VPC];
-#pragma unroll
-    for (int k = 0; k < VPC; k++) acc[k] = make_c<T>(0, 0);
-#pragma unroll
-    for (int k = 0; k < VPC; k++) {
-        const int nx = cover(u0 + k, 0, invx, 0, 1, ox, tx, 1);
-        for (int iz = 0; iz < nz; iz++)
-            for (int iy = 0; iy < ny; iy++) {
-                const int tyz = tz[iz] + ty[iy];
-                const size_t oyz = oz[iz] + oy[iy];
-                for (int ix = 0; ix < nx; ix++) {
-                    const int tile = tyz + tx[ix];
-                    if (tile < tile_lo || tile >= tile_hi) continue;
-                    for (int it = tile_start[tile]; it < tile_start[tile + 1]; it++) {   // tile_start = d_tile_items here
-                        const C c = scratch[(size_t)(it - item_lo) * PN + oyz + ox[ix]];
-                        acc[k].x += c.x; acc[k].y += c.y;
-                    }
-                }
-            }
-    }
+    int ty[3], oy[3], tz[3], oz[3];
+    const int ny = cover(u1, 1, geo.nb[0], PX, ty, oy);
+    const int nz = cover(u2, 2, geo.nb[0] * geo.nb[1], PX * PY, tz, oz);
+    // x: both cells of the pair lie in the same tile (bs[0] even, u0 even)
+    const int bs0 = geo.bs[0], nb0 = geo.nb[0];
+    const int t = (int)fastdiv((unsigned)u0, geo.inv_bs[0]), l = u0 - t * bs0;
+    const int len = (t == nb0 - 1) ? geo.Nt[0] - t * bs0 : bs0;
+    const int tp = t == 0 ? nb0 - 1 : t - 1, tn = t == nb0 - 1 ? 0 : t + 1;
+    const int lenp = (tp == nb0 - 1) ? geo.Nt[0] - tp * bs0 : bs0;
+    const bool p0 = l < MT, p1 = l + 1 < MT;                       // previous tile's high halo covers cell 0 / 1
+    const bool n0 = l >= len - MT, n1 = l + 1 >= len - MT && l + 1 < len;   // next tile's low halo
+    const bool c1 = l + 1 < len;                                   // second cell inside this tile's core
+    T a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+    auto add_tile = [&](int tile, int off, bool w0, bool w1) {
+        if (tile < tile_lo || tile >= tile_hi) return;
+        const int ia = tile_items[tile], ib = tile_items[tile + 1];
+        for (int it = ia; it < ib; it++) {
+            const C* sp = scratch + ((long long)(it - item_lo) * (long long)PN + off);
+            if (w0) { const C c = sp[0]; a0x += c.x; a0y += c.y; }
+            if (w1) { const C c = sp[1]; a1x += c.x; a1y += c.y; }
+        }
+    };
+    for (int iz = 0; iz < nz; iz++)
+        for (int iy = 0; iy < ny; iy++) {
+            const int tyz = tz[iz] + ty[iy];
+            const int oyz = oz[iz] + oy[iy];
+            add_tile(tyz + t, oyz + l + MT, true, c1);
+            if (p0) add_tile(tyz + tp, oyz + l + MT + lenp, true, p1);
+            if (n1 || n0) add_tile(tyz + tn, oyz + l + MT - len, n0, n1);
+        }
+    // a second cell beyond the core of a partial last tile belongs to the next tile (only if bs[0] is odd there)
     C* dst = g + (size_t)b * geo.gsz + ((size_t)u2 * geo.Nt[1] + u1) * geo.Nt[0] + u0;
-    if (VPC == 2) *reinterpret_cast<float4*>(dst) = make_float4((float)acc[0].x, (float)acc[0].y, (float)acc[VPC - 1].x, (float)acc[VPC - 1].y);
-    else dst[0] = acc[0];
+    if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4((float)a0x, (float)a0y, (float)a1x, (float)a1y);
+    else { dst[0] = make_c<T>(a0x, a0y); dst[1] = make_c<T>(a1x, a1y); }
 }
 
 // returns -1 if the tiled kernel does not apply, else a status; *wrote_all = true if every grid cell was
@@ -461,6 +465,7 @@ int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_l
     for (int d = 0; d < 3; d++) {
         const int last = geo.Nt[d] - (geo.nb[d] - 1) * geo.bs[d];
         if (geo.bs[d] < MT || last < MT) use_scratch = false;        // halos would reach past the neighbour
+        if (d == 0 && ((geo.bs[0] & 1) || (last & 1))) use_scratch = false;   // the gather works on x cell pairs
     }
     const size_t PN = (size_t)(geo.bs[0] + 2 * MT) * (geo.bs[1] + 2 * MT) * (geo.bs[2] + 2 * MT);
     const cudaStream_t st = p->stream;
@@ -488,8 +493,7 @@ int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_l
         CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SS_THREADS, smem, st>>>((const C*)fhat, (C*)g, (C*)p->d_tilebuf, (const T*)p->d_xs, p->d_perm,
                                             p->d_items, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
-        constexpr int VPC = 16 / (int)sizeof(C);
-        const int units = (geo.Nt[0] + VPC - 1) / VPC;
+        const int units = geo.Nt[0] / 2;                                   // Nt[0] is even; one thread per cell pair
         int bx = 32;
         while (bx < 256 && bx < units) bx <<= 1;
         dim3 gg((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "tile3d.cuh"
+#include "gather.cuh"
 #include "window.cuh"
 
 namespace {
