@@ -85,7 +85,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     from oracle import nfft_oracle as O
@@ -109,13 +109,13 @@ def run_reference(args, rank, world):
     val = 2 * w["M"] / t
     cb = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
           "sample": f"full workload, {args.steps} steps of forward+adjoint (M=2^21 each); plan {t_plan:.2f}s excluded"}
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "note": "reference algorithm restated in C/OpenMP + pocketfft (Julia unavailable)"},
         "cpu_baseline": cb,
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def main():
@@ -131,12 +131,21 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # library chatter (e.g. "NCCL version ...") must not reach stdout: the only stdout line is the JSON result
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
 
     if args.impl == "reference":
         if args.steps > 5:
             args.steps = 5
         args.warmup = min(args.warmup, 1)
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -282,9 +291,9 @@ def main():
         out["cpu_baseline"] = {"value": 2 * M / tc, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"full workload, {nrep} steps of forward+adjoint after 1 warm-up",
                                "ms_per_step": tc * 1e3}
-    print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    emit(out)
 
 
 if __name__ == "__main__":

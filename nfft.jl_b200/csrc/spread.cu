@@ -15,7 +15,6 @@
 #include "common.cuh"
 #include "window.cuh"
 #include "tile3d.cuh"
-#include "gather.cuh"
 
 namespace {
 

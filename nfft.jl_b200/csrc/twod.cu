@@ -10,7 +10,6 @@
 
 #include "common.cuh"
 #include "tile3d.cuh"
-#include "gather.cuh"
 #include "window.cuh"
 
 namespace {

@@ -1,9 +1,11 @@
 """Aggregates an `ncu --page source --csv` dump into hot SASS regions (instructions, samples, smem wavefronts)."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hdr = rows[1]; data = rows[2:]
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+end = starts[1] if len(starts) > 1 else len(rows)
+hdr = rows[1]; data = rows[2:end]
 ia = hdr.index('Instructions Executed'); isamp = hdr.index('# Samples'); isrc = hdr.index('Source')
-iw = hdr.index('L1 Wavefronts Shared'); iwi = hdr.index('L1 Wavefronts Shared Ideal')
+iw = hdr.index('L1 Wavefronts Shared') if 'L1 Wavefronts Shared' in hdr else isamp; iwi = hdr.index('L1 Wavefronts Shared Ideal') if 'L1 Wavefronts Shared Ideal' in hdr else isamp
 tot = sum(int(r[ia]) for r in data); tots = sum(int(r[isamp]) for r in data)
 print("total inst", tot, "n sass", len(data), "samples", tots)
 runs = []; cur = None

@@ -322,3 +322,51 @@ def test_tiled_1d_kernels(nb, N, T):
     f = O.random_complex(N, T, 3)
     assert rel(p.adjoint() * fHat, po.adjoint(fHat)) < TOL[T]
     assert rel(p * f, po.forward(f)) < TOL[T]
+
+
+import glob as _glob
+import os as _os
+
+
+@pytest.mark.parametrize("path", sorted(_glob.glob(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "*.npz"))))
+def test_against_committed_golden_vectors(nb, path):
+    """tests/golden/*.npz (oracle-generated, script committed): permutation bit-exact, outputs within tolerance"""
+    z = np.load(path)
+    N = tuple(int(n) for n in z["N"])
+    k = z["k"]
+    T = k.dtype.type
+    p = nb.plan_nfft(k.T, N, m=int(z["m"]), σ=2.0, precompute=nb.PrecomputeFlags(int(z["pre"])),
+                     blockSize=tuple(int(b) for b in z["blockSize"]))
+    assert np.array_equal(p.permutation()[0], z["perm"])
+    assert rel(p * z["f"], z["forward"]) < TOL[T]
+    assert rel(p.adjoint() * z["fHat"], z["adjoint"]) < TOL[T]
+
+
+def test_full_size_properties_c2(nb):
+    """BASELINE configs[1] at full size (3-D 128^3, M = 2^21, m = 3, Float32), through size-independent properties:
+    adjointness <A f, y> == <f, A^H y>, linearity, determinism of the adjoint (no atomics => bit-identical reruns),
+    and agreement with the NDFT on a subsample of nodes / image points."""
+    import torch
+    T = np.float32
+    N, M = (128, 128, 128), 2 ** 21
+    k = O.random_nodes(M, 3, T, seed=1)
+    p = nb.plan_nfft(torch.from_numpy(np.ascontiguousarray(k.T)).cuda(), N, m=3, σ=2.0)
+    perm, ts = p.permutation()
+    assert np.array_equal(np.sort(perm), np.arange(M)) and ts[-1] == M
+    key = O.tile_keys(O.shift_nodes(k), O.init_params(N, T, 3, 2.0, blockSize=p.params.blockSize))[0]
+    assert np.all(np.diff(key[perm]) >= 0)                                  # sorted by tile ...
+    same = key[perm][1:] == key[perm][:-1]
+    assert np.all(np.diff(perm)[same] > 0)                                  # ... and stable inside a tile
+    f = O.random_complex(N, T, 2)
+    y = O.random_complex(M, T, 3)
+    Af = p * f
+    AHy = p.adjoint() * y
+    lhs = np.vdot(y.astype(np.complex128), Af.astype(np.complex128))
+    rhs = np.vdot(AHy.astype(np.complex128).ravel(), f.astype(np.complex128).ravel())
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    f2 = O.random_complex(N, T, 4)
+    lin = p * np.asfortranarray(2 * f + 3j * f2)
+    assert rel(lin, 2 * Af + 3j * (p * f2)) < 1e-5
+    assert np.array_equal(AHy, p.adjoint() * y)                             # deterministic adjoint
+    sub = np.arange(0, M, M // 64)[:64]
+    assert rel(Af[sub], O.ndft(k[sub].astype(np.float64), f)) < 3e-5        # reference error level at m = 3, Float32
