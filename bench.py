@@ -186,11 +186,11 @@ def main():
         torch.cuda.synchronize()
 
     p.enable_timing(True)
+    sampler = ClockSampler(local_rank)     # samples SM clocks / throttle reasons from warm-up to the end of the e2e loop
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ts = nb.TimingStats()
     phases = {n: 0.0 for n in ("deconv", "fft", "conv", "conv_adjoint", "fft_adjoint", "deconv_adjoint")}
@@ -210,7 +210,6 @@ def main():
             kt[n] += v
     barrier()
     launches = p.launch_count() - l0
-    clocks = sampler.stop()
     t_step = sum(s.elapsed_time(e) for s, e in ev) / args.steps * 1e-3
     tt = torch.tensor([t_step], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -233,6 +232,7 @@ def main():
         nb.mul_(fo_p, p.adjoint(), fh_p)
     barrier()
     t_e2e = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
     te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
