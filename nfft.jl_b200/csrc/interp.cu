@@ -8,6 +8,10 @@
 //    weights are computed once per (node,dim,tap) into shared-memory records, then one warp per node
 //    gathers: lanes own the (y,x) taps of a plane and loop over the 2m z-planes (bank-conflict-free
 //    because a plane footprint spans 2m consecutive words per row), warp-shuffle reduction at the end.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "common.cuh"
 #include "window.cuh"
 #include "tile3d.cuh"
@@ -93,7 +97,7 @@ template <typename T, int MT> struct InterpLayout {
     __host__ __device__ size_t bytes() const
     {
         return sizeof(typename Cplx<T>::type) * (size_t)(PN + TI_WARPS * 32) + sizeof(T) * TI_WARPS * 32 * RW +
-               sizeof(int) * TI_WARPS * 64;
+               sizeof(int) * TI_WARPS * 64 + 16;
     }
 };
 
@@ -102,19 +106,20 @@ __global__ void __launch_bounds__(TI_THREADS)
 k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::type* __restrict__ fhat,
                const T* __restrict__ xs, const int32_t* __restrict__ perm,
                const int32_t* __restrict__ tile_start, int tile_lo, long long M, GeomDev geo,
-               WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp)
+               WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp, const __grid_constant__ CUtensorMap tmap, int use_tma)
 {
     using C = typename Cplx<T>::type;
     using RG = RowGeom<T, MT>;
     using IL = InterpLayout<T, MT>;
     constexpr int L = 2 * MT, VPC = RG::VPC, NV = RG::NV, NWX = RG::NWX, RW = IL::RW;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const IL lay(geo.bs);
     const int PX = lay.PX, PY = lay.PY, PZ = lay.PZ;
     C* tile = reinterpret_cast<C*>(smem_raw);                                   // [PN]
     C* res = tile + lay.PN;                                                     // [8][32]
     T* rec_w = reinterpret_cast<T*>(res + TI_WARPS * 32);                       // [8][32][RW]
     int* rec_i = reinterpret_cast<int*>(rec_w + TI_WARPS * 32 * RW);            // [8][32][2]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(rec_i + TI_WARPS * 64);
 
     const int32_t* item = tile_start + 3 * (size_t)(tile_lo + blockIdx.x);     // work item (tile, node range)
     const int tile_id = item[0];
@@ -127,9 +132,19 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     g += (long long)blockIdx.y * geo.gsz;
     fhat += (long long)blockIdx.y * M;
 
-    // toBlock!: stage the padded tile with cp.async; one warp per (z,y) row, lanes along x (coalesced row
-    // segments).  Everything that depends only on x is hoisted; (y,z) advance incrementally; no division.
-    {
+    // toBlock!: interior tiles (no periodic wrap) are staged by ONE TMA tensor-map load of the (PX,PY,PZ) box
+    // (cp.async.bulk.tensor + mbarrier); tiles that wrap are staged row by row with cp.async.
+    // (measured on B200: a box whose innermost start coordinate is not 16-byte aligned raises "illegal
+    //  instruction", so Float32 tiles qualify only when their origin x0 = tx*bs - m is even, i.e. m even)
+    const bool interior = use_tma && x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + PX <= geo.Nt[0] && y0 + PY <= geo.Nt[1] &&
+                          z0 + PZ <= geo.Nt[2] && ((x0 * (int)sizeof(C)) & 15) == 0;
+    if (interior) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            mbar_expect_tx(mbar, (unsigned)(sizeof(C) * PX * PY * PZ));
+            tma_load_4d(tile, &tmap, mbar, 2 * x0, y0, z0, (int)blockIdx.y);
+        }
+    } else {
         const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
         const int xg0 = wrapc(x0 + lane, geo.Nt[0], fw), xg1 = wrapc(x0 + lane + 32, geo.Nt[0], fw);
         const bool on0 = lane < PX, on1 = lane + 32 < PX;
@@ -170,6 +185,7 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     C* myres = res + warp * 32;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    if (interior) mbar_wait(mbar, 0);
 
     for (int rbase = n_lo + 32 * warp; rbase < n_hi; rbase += 32 * TI_WARPS) {
         const int nn = min(32, n_hi - rbase);
@@ -293,6 +309,39 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     }
 }
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor map of the (batched) grid seen as floats/doubles: dims (2*Nt0, Nt1, Nt2, B), box (2*PX, PY, PZ, 1)
+template <typename T> bool make_grid_tensor_map(CUtensorMap* tm, const void* g, const GeomDev& geo, int B, int PX, int PY, int PZ)
+{
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return false;
+    if (2 * PX > 256 || PY > 256 || PZ > 256 || ((uintptr_t)g & 15)) return false;
+    const cuuint64_t csz = 2 * sizeof(T);
+    cuuint64_t dims[4] = {(cuuint64_t)2 * geo.Nt[0], (cuuint64_t)geo.Nt[1], (cuuint64_t)geo.Nt[2], (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)geo.Nt[0] * csz, (cuuint64_t)geo.Nt[0] * geo.Nt[1] * csz, (cuuint64_t)geo.gsz * csz};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * PX), (cuuint32_t)PY, (cuuint32_t)PZ, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if ((strides[0] & 15) || ((box[0] * sizeof(T)) & 15)) return false;
+    const CUresult r = fn(tm, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4,
+                          const_cast<void*>(g), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 template <typename T, int MT>
 int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi)
 {
@@ -306,9 +355,12 @@ int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, 
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
     dim3 grid(item_hi - item_lo, B);
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    const int use_tma = (p->kernel_mode != 3 && make_grid_tensor_map<T>(&tmap, g, geo, B, lay.PX, lay.PY, lay.PZ)) ? 1 : 0;
     kern<<<grid, TI_THREADS, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm,
                                                p->d_items, item_lo, p->M, geo, make_win<T>(p),
-                                               make_poly_param<T, MT>(p));
+                                               make_poly_param<T, MT>(p), tmap, use_tma);
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;

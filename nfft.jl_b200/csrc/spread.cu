@@ -347,15 +347,33 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
             }
         }
         __syncthreads();
-        // flush: one vector RED (REDG.ADD.F32x2) per non-zero cell at the periodically wrapped position;
-        // x-dependent quantities hoisted, (y,z) advance incrementally, no division
+        if (SCRATCH) {
+            // the merged padded tile ("blocks[l]") leaves through the TMA engine: every (z,y) row is two bulk
+            // asynchronous copies shared -> global (cells [0,SX) from the low-x octant, [SX,PX) from the high-x
+            // one), issued by one thread per row; no register staging, no per-cell index math
+            const unsigned b0 = (unsigned)(SX * sizeof(C)), b1 = (unsigned)((PX - SX) * sizeof(C));
+            const bool bulk_ok = (b0 % 16 == 0) && (b1 % 16 == 0) && ((PX * sizeof(C)) % 16 == 0) && ((QX * sizeof(C)) % 16 == 0) &&
+                                 ((QN * sizeof(C)) % 16 == 0);
+            if (bulk_ok) {
+                fence_async_smem();
+                for (int row = threadIdx.x; row < PY * PZ; row += SS_THREADS) {
+                    const int z = row / PY, y = row - z * PY;
+                    const int oz_ = (NW == 8) ? (z >= SZ) : 0, oy_ = y >= SY;
+                    const C* pa = sub + (4 * oz_ + 2 * oy_) * QN + ((z - oz_ * SZ) * QY + (y - oy_ * SY)) * QX;
+                    C* sr = scratch + (size_t)row * PX;
+                    bulk_store_s2g(sr, pa, b0);
+                    bulk_store_s2g(sr + SX, pa + QN, b1);
+                }
+                bulk_commit_wait_read();
+                return;
+            }
+        }
+        // plain path (RED halo flush, or scratch rows that are not 16-byte granular)
         const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
         const int xa = lane, xb = lane + 32;
         const bool on0 = xa < PX, on1 = xb < PX;
         const int so0 = (xa < SX) ? xa : QN + xa - SX, so1 = (xb < SX) ? xb : QN + xb - SX;
         const int xg0 = wrapc(cx0 - MT + xa, geo.Nt[0], fw), xg1 = wrapc(cx0 - MT + xb, geo.Nt[0], fw);
-        // every warp walks all z-planes and owns rows y = warp + 8k of each (k unrolled => independent
-        // address chains in flight; with one CTA per SM the ILP has to come from inside the warp)
         for (int z = 0; z < PZ; z++) {
             const int oz_ = (NW == 8) ? (z >= SZ) : 0;
             const C* pz_ = sub + 4 * oz_ * QN + (z - oz_ * SZ) * QY * QX;
@@ -366,7 +384,7 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                 if (y < PY) {
                     const int oy_ = y >= SY;
                     const C* pa = pz_ + 2 * oy_ * QN + (y - oy_ * SY) * QX;
-                    if (SCRATCH) {     // plain coalesced stores of the merged padded tile ("blocks[l]")
+                    if (SCRATCH) {
                         C* sr = scratch + (z * PY + y) * PX;
                         if (on0) sr[xa] = pa[so0];
                         if (on1) sr[xb] = pa[so1];
@@ -381,10 +399,6 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     }
 }
 
-// addBlock! without the lock (/root/reference/src/convolution.jl:371-443): every grid cell sums, in a fixed
-// order, the <= 8 padded tiles (work items) that cover it and is written exactly once (so no memset of g either).
-// Preconditions checked on the host: every tile core is at least m cells long in every dimension, bs[0] even.
-// One CTA per (u1,u2) row segment: the y/z candidates are CTA-uniform, one thread handles two adjacent x cells.
 template <typename T, int MT>
 __global__ void __launch_bounds__(256)
 k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cplx<T>::type* __restrict__ g,

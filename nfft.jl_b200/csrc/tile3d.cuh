@@ -109,6 +109,49 @@ __device__ __forceinline__ void cp_async_cell(double2* dst, const double2* src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
+// bulk asynchronous copy shared -> global through the TMA engine (SASS: UBLKCP); size and both addresses must be
+// multiples of 16 bytes.  Completion is tracked with bulk async-groups.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) -- call after the CTA barrier
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMA tensor-map tile load (cp.async.bulk.tensor, SASS: UTMALDG) + mbarrier completion -------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_LOOP;\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// 4-D box (x, y, z, batch) of the grid -> dense shared-memory tile
+__device__ __forceinline__ void tma_load_4d(void* sdst, const void* tmap, unsigned long long* bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                   "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // 16-byte shared-memory unit <-> registers
 template <typename T> struct Unit;
 template <> struct Unit<float> {

@@ -1,0 +1,49 @@
+// TMA probe #3: raw PTX like the library, varying (a) static vs dynamic smem, (b) order of expect_tx vs copy, (c) coordinates
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+constexpr int SW = 32, SH = 16;
+__global__ void kern(const __grid_constant__ CUtensorMap tm, int x, int y, float* out, int variant, unsigned* info)
+{
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ alignas(128) float stat_buf[SH * SW];
+    __shared__ alignas(8) unsigned long long stat_bar;
+    float* tile = (variant & 1) ? (float*)dyn : stat_buf;
+    unsigned long long* bar = (variant & 1) ? (unsigned long long*)(dyn + SW * SH * 4) : &stat_bar;
+    unsigned sb = (unsigned)__cvta_generic_to_shared(bar), st = (unsigned)__cvta_generic_to_shared(tile);
+    if (threadIdx.x == 0) {
+        info[0] = st; info[1] = sb;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (variant & 2) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb), "r"(SW * SH * 4));
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(st), "l"(&tm), "r"(sb), "r"(x), "r"(y) : "memory");
+        if (!(variant & 2)) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb), "r"(SW * SH * 4));
+    }
+    __syncthreads();
+    asm volatile("{\n.reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@!p bra W;\n}\n" ::"r"(sb) : "memory");
+    for (int i = threadIdx.x; i < SW * SH; i += blockDim.x) out[i] = tile[i];
+}
+int main(int argc, char** argv)
+{
+    int variant = atoi(argv[1]); int x = atoi(argv[2]), y = atoi(argv[3]);
+    const int W = 128, H = 4096;
+    float* g; cudaMalloc(&g, (size_t)W * H * 4);
+    float* h = new float[W * H];
+    for (int i = 0; i < W * H; i++) h[i] = (float)i;
+    cudaMemcpy(g, h, (size_t)W * H * 4, cudaMemcpyHostToDevice);
+    float* out; cudaMalloc(&out, SW * SH * 4);
+    unsigned* info; cudaMalloc(&info, 16); cudaMemset(info, 0, 16);
+    CUtensorMap tm; memset(&tm, 0, sizeof(tm));
+    cuuint64_t dims[2] = {W, H}; cuuint64_t str[1] = {W * 4}; cuuint32_t box[2] = {SW, SH}; cuuint32_t es[2] = {1, 1};
+    CUresult r = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    kern<<<1, 128, SW * SH * 4 + 16>>>(tm, x, y, out, variant, info);
+    cudaError_t e = cudaDeviceSynchronize();
+    float o[2] = {0, 0}; unsigned inf[2] = {0, 0};
+    if (e == cudaSuccess) { cudaMemcpy(o, out, 8, cudaMemcpyDeviceToHost); cudaMemcpy(inf, info, 8, cudaMemcpyDeviceToHost); }
+    printf("variant %d (dyn=%d expect_first=%d) x=%d y=%d: encode=%d sync=%s first=%g expect=%g smem=0x%x bar=0x%x\n", variant, variant & 1, (variant >> 1) & 1,
+           x, y, (int)r, cudaGetErrorString(e), o[0], (double)(y * W + x), inf[0], inf[1]);
+    return 0;
+}
