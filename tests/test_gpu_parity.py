@@ -370,3 +370,54 @@ def test_full_size_properties_c2(nb):
     assert np.array_equal(AHy, p.adjoint() * y)                             # deterministic adjoint
     sub = np.arange(0, M, M // 64)[:64]
     assert rel(Af[sub], O.ndft(k[sub].astype(np.float64), f)) < 3e-5        # reference error level at m = 3, Float32
+
+
+def test_edge_cases(nb):
+    """empty / tiny / degenerate inputs the reference handles (ragged tiles, odd sizes, sigma != 2, clustered nodes)"""
+    T = np.float64
+    # no nodes at all
+    p = nb.plan_nfft(np.zeros((2, 0)), (16, 16), m=3, σ=2.0)
+    assert p.size_out() == (0,)
+    out = p.adjoint() * np.zeros(0, dtype=np.complex128)
+    assert out.shape == (16, 16) and not np.any(out)
+    assert (p * O.random_complex((16, 16), T, 1)).shape == (0,)
+    # one node, odd sizes, grid not a multiple of the tile, sigma = 1.5 and 1.25
+    for N, sig, m in [((33,), 1.5, 3), ((17, 21), 1.25, 4), ((9, 11, 13), 1.5, 2), ((70, 70), 2.0, 4), ((20, 18, 40), 2.0, 3)]:
+        for M in (1, 257):
+            k = O.random_nodes(M, len(N), T, seed=M)
+            p = nb.plan_nfft(k.T, N, m=m, σ=sig)
+            po = O.OraclePlan(k, N, m=m, sigma=sig, blockSize=p.params.blockSize)
+            assert p.Ñ == po.Nt and p.params.σ == po.p.sigma
+            assert np.array_equal(p.permutation()[0], po.perm)
+            fh = O.random_complex(M, T, 2); f = O.random_complex(N, T, 3)
+            assert rel(p.adjoint() * fh, po.adjoint(fh)) < 1e-12
+            assert rel(p * f, po.forward(f)) < 1e-12
+    # all nodes in one spot (every work item of one tile, one warp's sub-tile) and on exact cell boundaries
+    for N in [(64, 64), (32, 32, 32), (4096,)]:
+        D = len(N)
+        M = 9000
+        k = np.full((M, D), 0.123, dtype=np.float32) + (np.arange(M)[:, None] % 7) * np.float32(1e-4)
+        k[::3] = np.float32(0.25)                      # exactly on a grid cell
+        p = nb.plan_nfft(k.T, N, m=4 if D < 3 else 3, σ=2.0)
+        po = O.OraclePlan(k, N, m=4 if D < 3 else 3, sigma=2.0, blockSize=p.params.blockSize)
+        fh = O.random_complex(M, np.float32, 2); f = O.random_complex(N, np.float32, 3)
+        assert np.array_equal(p.permutation()[0], po.perm)
+        assert rel(p.adjoint() * fh, po.adjoint(fh)) < 1e-5
+        assert rel(p * f, po.forward(f)) < 1e-5
+
+
+@pytest.mark.parametrize("N", [(2048,), (96, 80)])
+def test_batched_1d_2d_and_regrow_nodes(nb, N):
+    T = np.float32
+    D, B = len(N), 3
+    M1, M2 = 5000, 12000
+    k1 = O.random_nodes(M1, D, T, seed=1); k2 = O.random_nodes(M2, D, T, seed=2)
+    p = nb.plan_nfft(k1.T, N, m=4, σ=2.0, ntransforms=B)
+    for k, M in ((k1, M1), (k2, M2), (k1, M1)):            # nodes! with growing and shrinking node counts
+        nb.nodes_(p, k.T)
+        po = O.OraclePlan(k, N, m=4, sigma=2.0, blockSize=p.params.blockSize)
+        f = O.random_complex(N + (B,), T, 4); fh = O.random_complex((M, B), T, 5)
+        out = p * f; adj = p.adjoint() * fh
+        for b in range(B):
+            assert rel(out[:, b], po.forward(np.asfortranarray(f[..., b]))) < 1e-5
+            assert rel(adj[..., b], po.adjoint(np.ascontiguousarray(fh[:, b]))) < 1e-5
