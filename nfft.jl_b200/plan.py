@@ -141,7 +141,14 @@ class B200NFFTPlan:
         N = tuple(int(n) for n in N)
         D = len(N)
         if dims is not None and tuple(dims) != tuple(range(1, D + 1)):
-            raise NotImplementedError("GPU NFFT does not work along directions right now!")  # ext/...:35-37
+            # directional plan (src/directional.jl, test/accuracy.jl:123-163): a transform over the LEADING dims
+            # 1:D-1 of an (N..., B) array is exactly a batched plan with ntransforms = B (batch slowest)
+            if tuple(dims) == tuple(range(1, D)) and D >= 2 and int(ntransforms) == 1:
+                ntransforms = N[-1]
+                N = N[:-1]
+                D -= 1
+            else:
+                raise NotImplementedError("GPU NFFT does not work along directions right now!")  # ext/...:35-37
         window = str(window).lstrip(":")
         if window != "kaiser_bessel":
             raise NotImplementedError(f"Window {window} not yet implemented!")
@@ -234,10 +241,10 @@ class B200NFFTPlan:
 
     # ---- interface.jl:170-211 -----------------------------------------------------------------
     def size_in(self):
-        return self.N
+        return self._bshape(self.N)
 
     def size_out(self):
-        return self.NOut
+        return self._bshape(self.NOut)
 
     def adjoint(self):
         return AdjointPlan(self)
@@ -596,6 +603,31 @@ def deconvolve_(p, f, g):
 
 def deconvolve_transpose_(p, g, f):
     return p.deconvolve_transpose_(g, f)
+
+
+def sdc(p, iters=20):
+    """NFFTTools.sdc (NFFTTools/src/samplingDensity.jl:59-155): Pipe-Menon density compensation weights through
+    the real-valued convolve_transpose!/convolve! pair, followed by the least-squares global scaling."""
+    T, J = p.T, p.J
+    weights = np.ones(J, dtype=T)
+    tmp = np.empty(J, dtype=T)
+    workg = np.empty(p.Ñ, dtype=T, order="F")
+    scaling = None
+    for i in range(iters):
+        convolve_transpose_(p, weights, workg)
+        if i == 0:
+            scaling = workg.max()
+        workg /= scaling
+        convolve_(p, workg, tmp)
+        tmp /= scaling
+        if np.any(tmp <= 0):
+            raise ValueError("non-positive weights")
+        weights /= tmp
+    u = np.ones(p.N, dtype=p.cT, order="F")
+    workf = (p * u) * weights
+    v = p.adjoint() * workf
+    c = float(np.real(v.sum()) / np.sum(np.abs(v) ** 2))
+    return (weights * T(c)).astype(T)
 
 
 def nfft(k, f, **kw):

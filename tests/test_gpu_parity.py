@@ -421,3 +421,29 @@ def test_batched_1d_2d_and_regrow_nodes(nb, N):
         for b in range(B):
             assert rel(out[:, b], po.forward(np.asfortranarray(f[..., b]))) < 1e-5
             assert rel(adj[..., b], po.adjoint(np.ascontiguousarray(fh[:, b]))) < 1e-5
+
+
+def test_sdc_function_and_directional_plan(nb):
+    """§8f-1: nb.sdc == NFFTTools.sdc known answer (test/samplingDensity.jl:10-27);  §8f-2: dims=1:2 of an (N1,N2,B)
+    array is the batched plan (test/accuracy.jl:123-163: equals looping the lower-dimensional NFFT)"""
+    N, T = (9, 8), np.float32
+    x = (np.arange(N[0]) / N[0] - 0.5).astype(T)
+    y = (np.arange(N[1]) / N[1] - 0.5).astype(T)
+    nodes = np.array([[a, b] for b in y for a in x], dtype=T).T
+    p = nb.plan_nfft(nodes, N, m=5, σ=2.0)
+    w = nb.sdc(p, iters=10)
+    assert w.dtype == T and np.all(w > 0) and np.allclose(w, 1 / 72, rtol=1e-4)
+    po = O.OraclePlan(nodes.T, N, m=5, sigma=2.0, blockSize=p.params.blockSize)
+    assert np.allclose(w, O.sdc(po, iters=10), rtol=1e-4)
+    # directional
+    N3 = (24, 20, 5)
+    k = O.random_nodes(700, 2, np.float64, seed=3)
+    pd = nb.plan_nfft(k.T, N3, m=5, σ=2.0, dims=range(1, 3))
+    assert pd.size_in() == N3 and pd.size_out() == (700, 5)
+    f = O.random_complex(N3, np.float64, 4)
+    out = pd * f
+    p2 = O.OraclePlan(k, N3[:2], m=5, sigma=2.0, blockSize=pd.params.blockSize)
+    for b in range(5):
+        assert rel(out[:, b], p2.forward(np.asfortranarray(f[..., b]))) < 1e-12
+    with pytest.raises(NotImplementedError):
+        nb.plan_nfft(k.T, N3, dims=range(2, 4))
