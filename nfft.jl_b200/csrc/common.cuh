@@ -76,6 +76,10 @@ struct nfftb200_plan {
     bool own_stream = false;
     cufftHandle fft = 0;
     bool have_fft = false;
+    // pruned 3-D FFT: 2-D FFTs only on the z-planes that hold image frequencies + 1-D FFT along z
+    cufftHandle fft_xy = 0, fft_z = 0;
+    bool have_pruned = false;
+    int64_t zlo_planes = 0, zhi_planes = 0;     // planes [0, zlo) and [Nt2 - zhi, Nt2) are the non-zero ones
 
     // host copies of the tables (double), for get_table and for re-upload
     std::vector<double> h_hat_inv;   // concatenated over d

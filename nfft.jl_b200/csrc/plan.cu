@@ -92,8 +92,68 @@ int make_fft(nfftb200_plan* p)
     return NFFTB200_OK;
 }
 
-int run_fft(nfftb200_plan* p, void* grid, int dir)
+// Pruned 3-D FFT (single GPU): the zero padding of D means that, in the forward transform, only the z-planes
+// u2 in [0, ceil(N2/2)) U [Nt2 - N2/2, Nt2) are non-zero before the FFT, and in the adjoint only those planes are
+// read after it.  So the 2-D (x,y) FFTs run on those planes only (two contiguous batches) and the 1-D FFT along z
+// runs on everything: 2/3 of the work of the full 3-D transform for sigma = 2.
+int make_fft_pruned(nfftb200_plan* p)
 {
+    p->have_pruned = false;
+    if (p->D != 3) return NFFTB200_OK;
+    const int64_t Na = p->N[2] / 2, Nb = (p->N[2] + 1) / 2;
+    if (Na + Nb > (3 * p->Nt[2]) / 4 || Na < 1) return NFFTB200_OK;       // not enough padding to pay off
+    p->zlo_planes = Nb; p->zhi_planes = Na;
+    const cufftType ty = p->dtype == NFFTB200_F32 ? CUFFT_C2C : CUFFT_Z2Z;
+    const long long plane = p->Nt[0] * p->Nt[1];
+    size_t ws = 0;
+    long long n2[2] = {p->Nt[1], p->Nt[0]};
+    if (cufftCreate(&p->fft_xy) != CUFFT_SUCCESS) return NFFTB200_OK;
+    // one plan with batch = max(Na, Nb) planes; the shorter range re-uses it through a second plan only if sizes differ
+    if (Na != Nb || cufftMakePlanMany64(p->fft_xy, 2, n2, nullptr, 1, plane, nullptr, 1, plane, ty, Nb, &ws) != CUFFT_SUCCESS) {
+        cufftDestroy(p->fft_xy); p->fft_xy = 0;
+        return NFFTB200_OK;                                                 // odd N2: keep the full plan
+    }
+    long long n1[1] = {p->Nt[2]}, emb[1] = {p->Nt[2]};
+    if (cufftCreate(&p->fft_z) != CUFFT_SUCCESS ||
+        cufftMakePlanMany64(p->fft_z, 1, n1, emb, plane, 1, emb, plane, 1, ty, plane, &ws) != CUFFT_SUCCESS) {
+        cufftDestroy(p->fft_xy); p->fft_xy = 0;
+        if (p->fft_z) { cufftDestroy(p->fft_z); p->fft_z = 0; }
+        return NFFTB200_OK;
+    }
+    cufftSetStream(p->fft_xy, p->stream);
+    cufftSetStream(p->fft_z, p->stream);
+    p->have_pruned = true;
+    return NFFTB200_OK;
+}
+
+template <typename CT, typename F> int pruned_exec(nfftb200_plan* p, CT* grid, int dir, F exec)
+{
+    const int cdir = dir < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;
+    const long long plane = p->Nt[0] * p->Nt[1];
+    for (int b = 0; b < p->B; b++) {
+        CT* gb = grid + (size_t)b * p->gsz;
+        CT* hi = gb + (size_t)(p->Nt[2] - p->zhi_planes) * plane;
+        if (dir < 0) {       // forward: 2-D on the non-zero planes, then z
+            CUFFT_TRY(p, exec(p->fft_xy, gb, gb, cdir));
+            CUFFT_TRY(p, exec(p->fft_xy, hi, hi, cdir));
+            CUFFT_TRY(p, exec(p->fft_z, gb, gb, cdir));
+        } else {             // adjoint: z on everything, then 2-D on the planes that are read
+            CUFFT_TRY(p, exec(p->fft_z, gb, gb, cdir));
+            CUFFT_TRY(p, exec(p->fft_xy, gb, gb, cdir));
+            CUFFT_TRY(p, exec(p->fft_xy, hi, hi, cdir));
+        }
+        p->launches += 3;
+    }
+    return NFFTB200_OK;
+}
+
+// pruned = true only from the mul! drivers (deconvolve -> FFT -> ... ), where the zero structure is known
+int run_fft(nfftb200_plan* p, void* grid, int dir, bool pruned = false)
+{
+    if (pruned && p->have_pruned && p->kernel_mode != 4) {
+        if (p->dtype == NFFTB200_F32) return pruned_exec<cufftComplex>(p, (cufftComplex*)grid, dir, cufftExecC2C);
+        return pruned_exec<cufftDoubleComplex>(p, (cufftDoubleComplex*)grid, dir, cufftExecZ2Z);
+    }
     const int cdir = dir < 0 ? CUFFT_FORWARD : CUFFT_INVERSE;
     if (p->dtype == NFFTB200_F32)
         CUFFT_TRY(p, cufftExecC2C(p->fft, (cufftComplex*)grid, (cufftComplex*)grid, cdir));
@@ -256,6 +316,7 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
         CUDA_TRY(p, cudaMalloc(&p->d_tile_start, sizeof(int32_t) * (size_t)(p->ntiles + 1)));
         CUDA_TRY(p, cudaMalloc(&p->d_flag, sizeof(int)));
         ST_TRY(make_fft(p));
+        ST_TRY(make_fft_pruned(p));
         return NFFTB200_OK;
     }();
     if (st != NFFTB200_OK) {
@@ -274,6 +335,7 @@ int nfftb200_destroy(nfftb200_plan* p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     nfftb_comm_destroy(p);
     if (p->have_fft) cufftDestroy(p->fft);
+    if (p->have_pruned) { cufftDestroy(p->fft_xy); cufftDestroy(p->fft_z); }
     void* bufs[] = {p->d_hat_inv, p->d_poly, p->d_lin, p->d_grid, p->d_xs, p->d_tile_start, p->d_keys[0],
                     p->d_keys[1], p->d_vals[0], p->d_vals[1], p->d_hist, p->d_flag, p->d_stage_f,
                     p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab, p->d_tilebuf, p->d_items, p->d_tile_items};
@@ -412,7 +474,7 @@ int nfftb200_exec_forward(nfftb200_plan* p, const void* f, void* fHat, int where
         rec(p, 0);
         ST_TRY(nfftb_deconvolve(p, df, p->d_grid, p->B));
         rec(p, 1);
-        ST_TRY(run_fft(p, p->d_grid, -1));
+        ST_TRY(run_fft(p, p->d_grid, -1, true));
         rec(p, 2);
         ST_TRY(nfftb_interp(p, p->d_grid, dh, p->B, 1, 0, p->ntiles));
         rec(p, 3);
@@ -437,7 +499,7 @@ int nfftb200_exec_adjoint(nfftb200_plan* p, const void* fHat, void* f, int where
         rec(p, 0);
         ST_TRY(nfftb_spread(p, dh, p->d_grid, p->B, 1, 0, p->ntiles));
         rec(p, 1);
-        ST_TRY(run_fft(p, p->d_grid, +1));
+        ST_TRY(run_fft(p, p->d_grid, +1, true));
         rec(p, 2);
         ST_TRY(nfftb_deconvolve_transpose(p, p->d_grid, df, p->B));
         rec(p, 3);
@@ -590,6 +652,7 @@ int nfftb200_set_stream(nfftb200_plan* p, void* cuda_stream)
     if (p->own_stream) { cudaStreamDestroy(p->stream); p->own_stream = false; }
     p->stream = (cudaStream_t)cuda_stream;
     CUFFT_TRY(p, cufftSetStream(p->fft, p->stream));
+    if (p->have_pruned) { CUFFT_TRY(p, cufftSetStream(p->fft_xy, p->stream)); CUFFT_TRY(p, cufftSetStream(p->fft_z, p->stream)); }
     return NFFTB200_OK;
 }
 
