@@ -127,9 +127,14 @@ int nfftb200_get_timing(nfftb200_plan* p, double out[7]);
  * (seconds, CUDA events on the plan's stream; needs set_timing(1)): out = {spread, interp, memset, 0} */
 int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
 
-/* kernel-selection knob for benchmarking/tests: 0 = auto (tiled shared-memory kernels where they apply;
- * the spreader stores per-tile sub-grids and a gather pass sums them: no global atomics), 1 = force the
- * generic global-RED kernels, 2 = tiled kernels with the halo flushed by vector REDs. */
+/* kernel-selection knob for benchmarking/tests:
+ *   0 = auto: tiled shared-memory kernels where they apply (spreader stores per-tile sub-grids with TMA bulk copies
+ *       and a gather pass sums them: no atomics; interpolator stages aligned interior tiles with a TMA tensor map;
+ *       3-D FFT pruned to the z-planes that carry image frequencies),
+ *   1 = force the generic warp-per-node kernels (global vector REDs),
+ *   2 = tiled spreader with the halo flushed by vector REDs instead of scratch + gather,
+ *   3 = auto, but the interpolator never uses the TMA tensor-map load,
+ *   4 = auto, but the full (unpruned) cuFFT plan. */
 int nfftb200_set_kernel_mode(nfftb200_plan* p, int mode);
 /* number of kernels + library calls this plan has launched so far */
 int nfftb200_get_launch_count(nfftb200_plan* p, int64_t* n);
