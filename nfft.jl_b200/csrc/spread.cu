@@ -12,6 +12,8 @@
 //    conflict-free by construction, deterministic order inside the tile.  Window weights are computed
 //    once per (node, dim, tap) by all threads into a double-buffered shared-memory record array.
 //    The finished tile (incl. halo) is flushed with one vector RED per cell (REDG.ADD.F32x2).
+#include <type_traits>
+
 #include "common.cuh"
 #include "window.cuh"
 #include "tile3d.cuh"
@@ -188,7 +190,7 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
             const int px = c0 - cx0 - ob0 * lay.SX + 1, py = c1 - cy0 - ob1 * lay.SY + 1,
                       pz = c2 - cz0 - ob2 * lay.SZ + 1;                          // first tap, padded sub-tile coords
             const int s = (VPC == 2) ? (px & 1) : 0;
-            mybase[lane] = (pz * QY + py) * QX + (px - s);
+            mybase[lane] = (((pz * QY + py) * QX + (px - s)) << 1) | s;      // low bit: row starts on an odd cell
             T r[RW];
 #pragma unroll
             for (int k = 0; k < NWX; k++) {
@@ -233,19 +235,26 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
         };
         fetch(0, wx, fa, fb, ra, rb, rwu, base);
         for (int n = 0; n < nn; n++) {
-            C* p0 = mysub + base;
+            C* p0 = mysub + (base >> 1);
             T wx2[NWX], fa2[NIT], fb2[NIT], ra2 = 0, rb2 = 0, rwu2[VPC];
             int base2 = base;
             if (RG::FULL_IT == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, fa2, fb2, ra2, rb2, rwu2, base2);
+            // Float32 rows that start on an even cell need one 16-byte unit less (the widened unit would only
+            // carry zero weights): node-uniform branch, saves a quarter of the shared-memory traffic of the row
+            auto full_iters = [&](auto nvu_tag) {
+                constexpr int NVU = decltype(nvu_tag)::value;
 #pragma unroll
-            for (int it = 0; it < RG::FULL_IT; it++) {
-                Unit<T> U[NV];
+                for (int it = 0; it < RG::FULL_IT; it++) {
+                    Unit<T> U[NVU];
 #pragma unroll
-                for (int u = 0; u < NV; u++) U[u].load(p0 + rowoff[it] + u * VPC);
-                if (it == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, fa2, fb2, ra2, rb2, rwu2, base2);
+                    for (int u = 0; u < NVU; u++) U[u].load(p0 + rowoff[it] + u * VPC);
+                    if (it == 0) fetch(n + 1 < nn ? n + 1 : n, wx2, fa2, fb2, ra2, rb2, rwu2, base2);
 #pragma unroll
-                for (int u = 0; u < NV; u++) { U[u].axpy(&wx[u * VPC], fa[it], fb[it]); U[u].store(p0 + rowoff[it] + u * VPC); }
-            }
+                    for (int u = 0; u < NVU; u++) { U[u].axpy(&wx[u * VPC], fa[it], fb[it]); U[u].store(p0 + rowoff[it] + u * VPC); }
+                }
+            };
+            if (VPC == 2 && NV > 1 && !(base & 1)) full_iters(std::integral_constant<int, (NV > 1 ? NV - 1 : 1)>{});
+            else full_iters(std::integral_constant<int, NV>{});
             if (RG::REM > 0 && rem_on) {
                 if (RG::SPLIT) { Unit<T> U; U.load(p0 + rem_off); U.axpy(rwu, ra, rb); U.store(p0 + rem_off); }
                 else {
