@@ -32,6 +32,19 @@ METRIC = "NFFT+adjoint nonuniform pts/sec"
 UNIT = "pts/s"
 
 
+def random_nodes(M, D, T, seed=1):
+    """SURVEY 8(d) synthetic nodes: uniform in [-1/2, 1/2), PCG64, cast once to T; shape (M, D)"""
+    rng = np.random.default_rng(seed)
+    return (rng.random((M, D)) - 0.5).astype(T)
+
+
+def random_complex(shape, T, seed=2):
+    rng = np.random.default_rng(seed)
+    cT = np.complex64 if T == np.float32 else np.complex128
+    a = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cT)
+    return np.asfortranarray(a) if a.ndim > 1 else a
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -88,16 +101,15 @@ class ClockSampler:
 def run_reference(args, rank, world, emit):
     if rank != 0:
         return
-    from oracle import nfft_oracle as O
-    from oracle.cpu_ref import CpuRefPlan, lib
+    from oracle.cpu_ref import CpuRefPlan, lib      # the reference arm is the one place that executes oracle/
     w = WORKLOAD
     cores = lib().ref_num_threads()
-    k = O.random_nodes(w["M"], 3, w["T"], seed=1)
+    k = random_nodes(w["M"], 3, w["T"], seed=1)
     t0 = time.perf_counter()
     p = CpuRefPlan(k, w["N"], m=w["m"], sigma=w["sigma"], workers=cores)
     t_plan = time.perf_counter() - t0
-    f = O.random_complex(w["N"], w["T"], 2)
-    fh = O.random_complex(w["M"], w["T"], 3)
+    f = random_complex(w["N"], w["T"], 2)
+    fh = random_complex(w["M"], w["T"], 3)
     for _ in range(args.warmup):
         p.forward(f); p.adjoint(fh)
     times = []
@@ -151,7 +163,6 @@ def main():
     import torch
     import torch.distributed as dist
     import nfft_jl_b200 as nb
-    from oracle import nfft_oracle as O   # only for the synthetic inputs and the cpu_baseline leg
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -159,7 +170,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     w = WORKLOAD
     N, M, T = w["N"], w["M"], w["T"]
-    k = O.random_nodes(M, 3, T, seed=1)                     # same nodes on every rank (shared by the batch)
+    k = random_nodes(M, 3, T, seed=1)                       # same nodes on every rank (shared by the batch)
     kd = torch.from_numpy(np.ascontiguousarray(k.T)).cuda()
     bsz = tuple(int(x) for x in args.block_size.split(",")) if args.block_size else None
     if world > 1:      # batched plan with ntransforms = world, one transform per rank, no data-path collective
@@ -168,8 +179,8 @@ def main():
     else:
         p = nb.plan_nfft(kd, N, m=w["m"], σ=w["sigma"], blockSize=bsz)
     p.set_kernel_mode(args.kernel_mode)
-    f_h = O.random_complex(N, T, 100 + rank)
-    fh_h = O.random_complex(M, T, 200 + rank)
+    f_h = random_complex(N, T, 100 + rank)
+    fh_h = random_complex(M, T, 200 + rank)
     f = p.empty_image(); f.copy_(torch.from_numpy(np.ascontiguousarray(f_h.T)).cuda().permute(2, 1, 0))
     fh = p.empty_out(); fh.copy_(torch.from_numpy(fh_h).cuda())
     f_out = p.empty_image()
