@@ -12,6 +12,9 @@ CFG = {
     "C3": dict(N=(512, 512), M=2 ** 20, m=4, T=np.float32, B=4, nodes="radial"),
     "C4s": dict(N=(2 ** 20,), M=2 ** 23, m=4, T=np.float64, B=1, nodes="random"),
     "C5s": dict(N=(256, 256, 256), M=2 ** 24, m=3, T=np.float32, B=1, nodes="random"),
+    "C3full": dict(N=(512, 512), M=2 ** 20, m=4, T=np.float32, B=32, nodes="radial"),
+    "C4": dict(N=(2 ** 22,), M=2 ** 25, m=4, T=np.float64, B=1, nodes="random"),
+    "C5": dict(N=(256, 256, 256), M=2 ** 27, m=3, T=np.float32, B=1, nodes="random"),
 }
 names = sys.argv[1:] or ["C1", "C2", "C3", "C4s"]
 for name in names:
