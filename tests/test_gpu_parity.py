@@ -447,3 +447,18 @@ def test_sdc_function_and_directional_plan(nb):
         assert rel(out[:, b], p2.forward(np.asfortranarray(f[..., b]))) < 1e-12
     with pytest.raises(NotImplementedError):
         nb.plan_nfft(k.T, N3, dims=range(2, 4))
+
+
+def test_multi_gpu_node_and_batch_sharding():
+    """node sharding (reduce-scatter + slab FFT + all-gather) and batch sharding on 2 GPUs vs the oracle; skipped on
+    single-GPU boxes (run manually with `gpurun --gpus 2`)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29561",
+                          _os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert "MGPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
