@@ -84,7 +84,7 @@ k_spread_generic(const void* __restrict__ fhat_, void* __restrict__ g_, const T*
 // ---------------------------------------------------------------------------------------
 // tiled 3-D spreader: warp-private padded sub-tiles, row-per-lane accumulation
 // ---------------------------------------------------------------------------------------
-constexpr int SS_CHUNK = 1024;       // nodes whose octant ids are cached per pass
+constexpr int SS_CHUNK = 512;        // nodes staged per pass (coordinates, values, octant ids in shared memory)
 
 // NW = 8: octants 2x2x2, one CTA per SM;  NW = 4: quadrants 2x2x1 (for tiles that are half as thick), two CTAs
 // per SM so that one CTA's shared-memory-bound accumulation overlaps the other's weight/merge/flush phases.
@@ -102,7 +102,8 @@ template <typename T, int MT, int NW> struct SubLayout {
     __host__ __device__ size_t bytes() const
     {
         return sizeof(typename Cplx<T>::type) * (size_t)NW * QN + sizeof(T) * NW * 32 * RW +
-               sizeof(int) * NW * 32 + sizeof(unsigned short) * NW * 64 + SS_CHUNK;
+               sizeof(int) * NW * 32 + sizeof(unsigned short) * NW * 64 + SS_CHUNK +
+               sizeof(T) * 3 * SS_CHUNK + sizeof(typename Cplx<T>::type) * SS_CHUNK + 16;
     }
 };
 
@@ -127,6 +128,8 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     int* rec_b = reinterpret_cast<int*>(rec_w + SS_WARPS * 32 * RW);            // [8][32]
     unsigned short* list = reinterpret_cast<unsigned short*>(rec_b + SS_WARPS * 32);   // [8][64]
     unsigned char* oct = reinterpret_cast<unsigned char*>(list + SS_WARPS * 64);      // [SS_CHUNK]
+    C* s_v = reinterpret_cast<C*>(oct + SS_CHUNK);                                     // [SS_CHUNK] node values (staged)
+    T* s_x = reinterpret_cast<T*>(s_v + SS_CHUNK);                                     // [SS_CHUNK][3] shifted coordinates (staged)
 
     // blockIdx.x walks work items (tile, node range); tile_start is the item table here
     const int32_t* item = tile_start + 3 * (size_t)(tile_lo + blockIdx.x);
@@ -148,12 +151,6 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     T* myrec = rec_w + warp * 32 * RW;
     int* mybase = rec_b + warp * 32;
     unsigned short* mylist = list + warp * 64;
-
-    {   // zero all sub-tiles with 16-byte stores
-        uint4* z = reinterpret_cast<uint4*>(sub);
-        const int n16 = (int)((sizeof(C) * (size_t)SS_WARPS * QN) / 16);
-        for (int q = threadIdx.x; q < n16; q += SS_THREADS) z[q] = make_uint4(0, 0, 0, 0);
-    }
 
     // per-lane constant row geometry
     int rowoff[RG::FULL_IT > 0 ? RG::FULL_IT : 1], wyo[RG::FULL_IT > 0 ? RG::FULL_IT : 1],
@@ -177,16 +174,16 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     auto process_round = [&](int cbase, int nn) {
         // ---- phase A: lane-per-node weights and record
         if (lane < nn) {
-            const long long i = (long long)cbase + mylist[lane];
+            const int q = mylist[lane];                       // chunk-local node index: everything is staged in smem
             T ks0, ks1, ks2;
-            const int c0 = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks0);
-            const int c1 = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks1);
-            const int c2 = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks2);
+            const int c0 = node_cell<T>(s_x[q * 3 + 0], geo.Nt[0], ks0);
+            const int c1 = node_cell<T>(s_x[q * 3 + 1], geo.Nt[1], ks1);
+            const int c2 = node_cell<T>(s_x[q * 3 + 2], geo.Nt[2], ks2);
             T w0[L], w1[L], w2[L];
             eval_taps<T, MT>(win, pp, ks0, c0, w0);
             eval_taps<T, MT>(win, pp, ks1, c1, w1);
             eval_taps<T, MT>(win, pp, ks2, c2, w2);
-            const C v = fhat[perm[i]];
+            const C v = s_v[q];
             const int px = c0 - cx0 - ob0 * lay.SX + 1, py = c1 - cy0 - ob1 * lay.SY + 1,
                       pz = c2 - cz0 - ob2 * lay.SZ + 1;                          // first tap, padded sub-tile coords
             const int s = (VPC == 2) ? (px & 1) : 0;
@@ -275,14 +272,38 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
 
     for (int cbase = n_lo; cbase < n_hi; cbase += SS_CHUNK) {
         const int nc = min(SS_CHUNK, n_hi - cbase);
-        __syncthreads();                                   // oct[] free, sub-tiles zeroed
-        for (int q = threadIdx.x; q < nc; q += SS_THREADS) {
-            const long long i = (long long)cbase + q;
-            T ks;
-            const int l0 = node_cell<T>(xs[i * 3 + 0], geo.Nt[0], ks) - cx0;
-            const int l1 = node_cell<T>(xs[i * 3 + 1], geo.Nt[1], ks) - cy0;
-            const int l2 = node_cell<T>(xs[i * 3 + 2], geo.Nt[2], ks) - cz0;
-            oct[q] = (unsigned char)((l0 >= lay.SX) + 2 * (l1 >= lay.SY) + ((NW == 8) ? 4 * (l2 >= lay.SZ) : 0));
+        __syncthreads();                                   // staging arrays free
+        // stage the chunk: issue all global loads (coordinates, permutation -> value gather) first, zero the
+        // sub-tiles while they are in flight (first chunk), then consume them -- phase A has no global loads left
+        constexpr int NPT = SS_CHUNK / SS_THREADS;         // nodes per thread
+        T rx[NPT][3];
+        C rv[NPT];
+#pragma unroll
+        for (int k = 0; k < NPT; k++) {
+            const int q = threadIdx.x + k * SS_THREADS;
+            if (q < nc) {
+                const long long i = (long long)cbase + q;
+                rx[k][0] = xs[i * 3 + 0]; rx[k][1] = xs[i * 3 + 1]; rx[k][2] = xs[i * 3 + 2];
+                rv[k] = fhat[perm[i]];
+            }
+        }
+        if (cbase == n_lo) {   // zero all sub-tiles with 16-byte stores
+            uint4* z = reinterpret_cast<uint4*>(sub);
+            const int n16 = (int)((sizeof(C) * (size_t)SS_WARPS * QN) / 16);
+            for (int q = threadIdx.x; q < n16; q += SS_THREADS) z[q] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < NPT; k++) {
+            const int q = threadIdx.x + k * SS_THREADS;
+            if (q < nc) {
+                T ks;
+                const int l0 = node_cell<T>(rx[k][0], geo.Nt[0], ks) - cx0;
+                const int l1 = node_cell<T>(rx[k][1], geo.Nt[1], ks) - cy0;
+                const int l2 = node_cell<T>(rx[k][2], geo.Nt[2], ks) - cz0;
+                oct[q] = (unsigned char)((l0 >= lay.SX) + 2 * (l1 >= lay.SY) + ((NW == 8) ? 4 * (l2 >= lay.SZ) : 0));
+                s_x[q * 3 + 0] = rx[k][0]; s_x[q * 3 + 1] = rx[k][1]; s_x[q * 3 + 2] = rx[k][2];
+                s_v[q] = rv[k];
+            }
         }
         __syncthreads();
         int cnt = 0;
