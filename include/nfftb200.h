@@ -52,8 +52,15 @@ enum { NFFTB200_F32 = 0, NFFTB200_F64 = 1 };
  *   TENSOR     -> numerically identical to POLYNOMIAL (precomputation.jl:556-591); evaluated on the fly */
 enum { NFFTB200_FULL = 1, NFFTB200_TENSOR = 2, NFFTB200_LINEAR = 3, NFFTB200_POLYNOMIAL = 4 };
 
-/* window=:kaiser_bessel (src/windowFunctions.jl:21-39) is the only window of this path */
-enum { NFFTB200_KAISER_BESSEL = 0 };
+/* window pairs of getWindow (src/windowFunctions.jl:4-19): :kaiser_bessel (default, :21-39), :gauss (:60-73),
+ * :spline (:75-99), :kaiser_bessel_rev (:41-57), :cosh_type (:104-134) */
+enum {
+    NFFTB200_KAISER_BESSEL = 0,
+    NFFTB200_GAUSS = 1,
+    NFFTB200_SPLINE = 2,
+    NFFTB200_KAISER_BESSEL_REV = 3,
+    NFFTB200_COSH_TYPE = 4
+};
 
 /* where caller buffers live */
 enum { NFFTB200_HOST = 0, NFFTB200_DEVICE = 1 };

@@ -33,6 +33,8 @@ template <typename T> struct WinDev {
     int mode;          // NFFTB200_FULL / LINEAR / POLYNOMIAL (TENSOR is mapped to POLYNOMIAL)
     int lin_scale;     // LUTSize / m
     T b;               // Kaiser-Bessel shape parameter pi*(2-1/sigma) in T
+    int window;        // NFFTB200_KAISER_BESSEL ... NFFTB200_COSH_TYPE (used by the FULL mode only)
+    T beta;            // cosh_type: pi*m*(2-1/sigma) in T
     const T* poly;     // (2m+1) x 2m, column-major (column = tap)
     const T* lin;      // LUTSize + 2
 };
@@ -58,6 +60,8 @@ struct nfftb200_plan {
     double sigma = 2.0;       // effective sigma = Nt[0]/N[0] rounded to T
     double reltol = 1e-9;
     double b = 0.0;           // window shape parameter as evaluated in T
+    double beta = 0.0;        // cosh_type shape parameter pi*m*(2-1/sigma) as evaluated in T
+    int window = NFFTB200_KAISER_BESSEL;
     int precompute = NFFTB200_POLYNOMIAL;
     int B = 1;                // ntransforms
     int device = 0;
@@ -191,6 +195,8 @@ template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
     w.mode = (p->precompute == NFFTB200_TENSOR) ? NFFTB200_POLYNOMIAL : p->precompute;
     w.lin_scale = (int)(p->lut_size / p->m);
     w.b = (T)p->b;
+    w.window = p->window;
+    w.beta = (T)p->beta;
     w.poly = (const T*)p->d_poly;
     w.lin = (const T*)p->d_lin;
     return w;

@@ -253,8 +253,8 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
     *out = nullptr;
     if (D < 1 || D > NFFTB_MAX_D) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "only D = 1, 2, 3 are supported");
     if (dtype != NFFTB200_F32 && dtype != NFFTB200_F64) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "dtype");
-    if (window != NFFTB200_KAISER_BESSEL)
-        return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "Window not yet implemented! (only :kaiser_bessel)");
+    if (window < NFFTB200_KAISER_BESSEL || window > NFFTB200_COSH_TYPE)
+        return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "Window not yet implemented!");
     if (precompute < NFFTB200_FULL || precompute > NFFTB200_POLYNOMIAL)
         return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "precompute flag not supported");
     if (m < 1 || m > NFFTB_MAX_M) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "m must be in 1..8");
@@ -262,7 +262,7 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
     if (ntransforms < 1) return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "ntransforms must be >= 1");
 
     nfftb200_plan* p = new nfftb200_plan();
-    p->D = D; p->dtype = dtype; p->m = m; p->precompute = precompute; p->B = ntransforms; p->device = device;
+    p->D = D; p->dtype = dtype; p->m = m; p->precompute = precompute; p->B = ntransforms; p->device = device; p->window = window;
     // initParams, src/precomputation.jl:14-29
     static const int m2K[9] = {1, 3, 7, 9, 14, 17, 20, 23, 24};
     p->lut_size = ((int64_t)1 << m2K[std::min(m + 1, 9) - 1]) * m;
@@ -277,9 +277,11 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
         const float s = (float)((double)p->Nt[0] / (double)p->N[0]);
         p->sigma = s;
         p->b = (double)((float)M_PI * (2.0f - 1.0f / s));       // pi*(2-1/sigma) evaluated in Float32
+        p->beta = (double)((float)M_PI * (float)m * (2.0f - 1.0f / s));
     } else {
         p->sigma = (double)p->Nt[0] / (double)p->N[0];
         p->b = M_PI * (2.0 - 1.0 / p->sigma);
+        p->beta = M_PI * (double)m * (2.0 - 1.0 / p->sigma);
     }
     if (block_size) {
         for (int d = 0; d < D; d++) {

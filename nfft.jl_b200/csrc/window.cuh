@@ -53,6 +53,55 @@ template <typename T> __device__ __forceinline__ T kb_exact(T x, int m, T b)
     return b / (T)3.141592653589793238462643383279502884;
 }
 
+__device__ __forceinline__ float texp(float a) { return expf(a); }
+__device__ __forceinline__ double texp(double a) { return exp(a); }
+__device__ __forceinline__ float tcosh(float a) { return coshf(a); }
+__device__ __forceinline__ double tcosh(double a) { return cosh(a); }
+__device__ __forceinline__ float ti0(float a) { return cyl_bessel_i0f(a); }
+__device__ __forceinline__ double ti0(double a) { return cyl_bessel_i0(a); }
+
+// exact window in grid units for the FULL mode, any window of getWindow
+// (/root/reference/src/windowFunctions.jl:41-116); every window but kaiser_bessel is 0 for |x| >= m
+template <typename T> __device__ __noinline__ T win_other(T x, int m, const WinDev<T>& w)
+{
+    const T mm = (T)m;
+    const T pi = (T)3.141592653589793238462643383279502884;
+    if (!(fabs(x) < mm)) return (T)0;
+    if (w.window == NFFTB200_GAUSS) {
+        const T b = mm / pi;
+        return (T)1 / tsqrt(pi * b) * texp(-(x * x) / b);
+    }
+    if (w.window == NFFTB200_KAISER_BESSEL_REV) {
+        const T q = x / mm;
+        return (T)0.5 / mm * ti0(mm * w.b * tsqrt((T)1 - q * q));
+    }
+    if (w.window == NFFTB200_COSH_TYPE) {
+        const T q = x / mm;
+        const T alpha = tsqrt((T)1 - q * q);
+        return (T)1 / (tcosh(w.beta) - (T)1) * (tcosh(w.beta * alpha) - (T)1) / alpha;
+    }
+    // spline: cardinal B-spline of order 2m at x + m, Cox-de Boor bottom-up
+    const T k = x + mm;
+    const int order = 2 * m;
+    T a[2 * NFFTB_MAX_M];
+    for (int j = 0; j < 2 * NFFTB_MAX_M; j++) {
+        const T kj = k - (T)j;
+        a[j] = (j < order && kj >= (T)0 && kj < (T)1) ? (T)1 : (T)0;
+    }
+    for (int n = 2; n <= order; n++)
+        for (int j = 0; j + n <= order; j++) {
+            const T kj = k - (T)j;
+            a[j] = kj / (T)(n - 1) * a[j] + ((T)n - kj) / (T)(n - 1) * a[j + 1];
+        }
+    return a[0];
+}
+
+template <typename T> __device__ __forceinline__ T win_exact(T x, int m, const WinDev<T>& w)
+{
+    if (w.window == NFFTB200_KAISER_BESSEL) return kb_exact<T>(x, m, w.b);
+    return win_other<T>(x, m, w);
+}
+
 // weights of the 2m taps of one dimension; tap l sits at cell (c - m + 1 + l)
 template <typename T>
 __device__ __forceinline__ void node_taps(const WinDev<T>& w, T kscale, int c, T* __restrict__ out)
@@ -83,7 +132,7 @@ __device__ __forceinline__ void node_taps(const WinDev<T>& w, T kscale, int c, T
             out[l] = add_rn(v1, mul_rn(alpha, sub_rn(v2, v1)));
         }
     } else {
-        for (int l = 0; l < L; l++) out[l] = kb_exact<T>(sub_rn(d0, (T)l), m, w.b);
+        for (int l = 0; l < L; l++) out[l] = win_exact<T>(sub_rn(d0, (T)l), m, w);
     }
 }
 
@@ -112,5 +161,5 @@ __device__ __forceinline__ T node_tap(const WinDev<T>& w, T kscale, int c, int l
         const T v1 = w.lin[a1], v2 = w.lin[a2];
         return add_rn(v1, mul_rn(alpha, sub_rn(v2, v1)));
     }
-    return kb_exact<T>(sub_rn(d0, (T)l), m, w.b);
+    return win_exact<T>(sub_rn(d0, (T)l), m, w);
 }

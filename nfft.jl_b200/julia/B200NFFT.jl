@@ -56,6 +56,9 @@ mutable struct B200NFFTPlan{T,D} <: AbstractNFFTPlan{T,D,1}
     ntransforms::Int
 end
 
+# order of the NFFTB200_* window enum in include/nfftb200.h
+const WINDOWS = (:kaiser_bessel, :gauss, :spline, :kaiser_bessel_rev, :cosh_type)
+
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float64}) = Cint(1)
 
@@ -65,7 +68,8 @@ function B200NFFTPlan(k::Matrix{T}, N::NTuple{D,Int}; dims::Union{Integer,UnitRa
                       sortNodes=false, storeDeconvolutionIdx=false, blocking=true, fftflags=nothing,
                       kwargs...) where {T<:Union{Float32,Float64},D}
     dims == 1:D || error("GPU NFFT does not work along directions right now!")   # ext/...:35-37
-    window == :kaiser_bessel || error("Window $(window) not yet implemented!")    # src/windowFunctions.jl:16
+    wcode = findfirst(==(window), WINDOWS)                                        # src/windowFunctions.jl:4-19
+    wcode === nothing && error("Window $(window) not yet implemented!")
     size(k, 1) == D || throw(ArgumentError("Nodes x have dimension $(size(k,1)) != $D"))
     m, σ, reltol = accuracyParams(; kwargs...)                                    # AbstractNFFTs/src/misc.jl:66-81
     h = Ref{Ptr{Cvoid}}(C_NULL)
@@ -73,7 +77,7 @@ function B200NFFTPlan(k::Matrix{T}, N::NTuple{D,Int}; dims::Union{Integer,UnitRa
     bs = blockSize === nothing ? C_NULL : pointer(collect(Int64, blockSize))
     st = ccall((:nfftb200_plan_create, libnfftb200), Cint,
                (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cdouble, Cint, Cint, Cint, Ptr{Int64}, Cint),
-               h, D, Nv, dtype_code(T), m, σ, 0, Int(precompute), ntransforms, bs, device)
+               h, D, Nv, dtype_code(T), m, σ, wcode - 1, Int(precompute), ntransforms, bs, device)
     check(C_NULL, st)
     Ñv = zeros(Int64, D); bsv = zeros(Int64, D)
     nt = Ref{Int64}(0); lut = Ref{Int64}(0); sg = Ref{Cdouble}(0); M = Ref{Int64}(0)

@@ -41,6 +41,10 @@ class DimensionMismatch(ValueError):
     """Julia's DimensionMismatch"""
 
 
+# getWindow symbols (src/windowFunctions.jl:4-19) in the order of the NFFTB200_* window enum
+WINDOWS = ("kaiser_bessel", "gauss", "spline", "kaiser_bessel_rev", "cosh_type")
+
+
 class PrecomputeFlags(enum.IntEnum):
     """AbstractNFFTs/src/misc.jl:13-18"""
     FULL = 1
@@ -150,8 +154,8 @@ class B200NFFTPlan:
             else:
                 raise NotImplementedError("GPU NFFT does not work along directions right now!")  # ext/...:35-37
         window = str(window).lstrip(":")
-        if window != "kaiser_bessel":
-            raise NotImplementedError(f"Window {window} not yet implemented!")
+        if window not in WINDOWS:
+            raise NotImplementedError(f"Window {window} not yet implemented!")      # src/windowFunctions.jl:16
         k_is_torch = _is_torch(k)
         kshape = tuple(k.shape)
         if len(kshape) == 1:
@@ -191,7 +195,7 @@ class B200NFFTPlan:
         self._h = C.c_void_p()
         Narr = (C.c_int64 * D)(*N)
         bs = (C.c_int64 * D)(*[int(b) for b in blockSize]) if blockSize is not None else None
-        st = self._L.nfftb200_plan_create(C.byref(self._h), D, Narr, 0 if T == np.float32 else 1, m_, σ_, 0,
+        st = self._L.nfftb200_plan_create(C.byref(self._h), D, Narr, 0 if T == np.float32 else 1, m_, σ_, WINDOWS.index(window),
                                           int(precompute), self.ntransforms, bs, self.device)
         _check(None, st)
         Nt = (C.c_int64 * D)()

@@ -89,6 +89,7 @@ class Params:
     blockSize: tuple
     precompute: int
     b: float             # Kaiser-Bessel shape parameter, evaluated in T
+    window: str = "kaiser_bessel"
 
     @property
     def D(self):
@@ -96,7 +97,7 @@ class Params:
 
 
 def init_params(N, T=np.float64, m=None, sigma=None, reltol=None, precompute=POLYNOMIAL,
-                blockSize=None):
+                blockSize=None, window="kaiser_bessel"):
     """src/precomputation.jl:3-56 (dims = 1:D only)."""
     N = tuple(int(n) for n in N)
     m, sigma, reltol = accuracy_params(m, sigma, reltol)
@@ -112,8 +113,10 @@ def init_params(N, T=np.float64, m=None, sigma=None, reltol=None, precompute=POL
     blockSize = tuple(int(b) for b in blockSize)
     # b = pi*(2-1/sigma) with sigma::T  => evaluated in T (src/windowFunctions.jl:23)
     b = T(np.pi) * (T(2) - T(1) / sig_eff) if T == np.float32 else np.pi * (2.0 - 1.0 / float(sig_eff))
+    if window not in WINDOWS:
+        raise ValueError("Window %s not yet implemented!" % window)       # src/windowFunctions.jl:16
     return Params(T=T, N=N, Nt=Nt, m=m, sigma=float(sig_eff), reltol=reltol, LUTSize=LUTSize,
-                  blockSize=blockSize, precompute=precompute, b=float(T(b)))
+                  blockSize=blockSize, precompute=precompute, b=float(T(b)), window=window)
 
 
 # --------------------------------------------------------------------------------------
@@ -137,6 +140,129 @@ def window_kaiser_bessel_hat(n, Nt, m, b):
     """src/windowFunctions.jl:36-39 (always evaluated in Float64, see module docstring)."""
     n = np.asarray(n, dtype=np.float64)
     return _special.i0(m * np.sqrt(float(b) ** 2 - (2.0 * np.pi * n / Nt) ** 2))
+
+
+# --------------------------------------------------------------------------------------
+# the other window pairs (src/windowFunctions.jl:41-134), all in *grid units* x = N-tilde*k
+# --------------------------------------------------------------------------------------
+WINDOWS = ("kaiser_bessel", "gauss", "spline", "kaiser_bessel_rev", "cosh_type")
+
+
+def window_kaiser_bessel_rev(x, m, b, dtype=np.float64):
+    """src/windowFunctions.jl:41-50: 0.5/m * I0(m b sqrt(1-(x/m)^2)) for |x| < m, else 0."""
+    x = np.asarray(x, dtype=dtype)
+    mm, bb = dtype(m), dtype(b)
+    inside = np.abs(x) < mm
+    arg = mm * bb * np.sqrt(np.where(inside, dtype(1) - (x / mm) ** 2, dtype(0)))
+    y = dtype(0.5) / mm * _special.i0(arg.astype(np.float64)).astype(dtype)
+    return np.where(inside, y, dtype(0)).astype(dtype)
+
+
+def window_kaiser_bessel_rev_hat(n, Nt, m, b):
+    """src/windowFunctions.jl:52-57: real(sinc(sqrt(complex((2 pi m n/Nt)^2-(m b)^2))/pi)),
+    i.e. sinh(a)/a below the cut-off and sin(a)/a above it."""
+    n = np.asarray(n, dtype=np.float64)
+    q = (2.0 * np.pi * m * n / Nt) ** 2 - (m * float(b)) ** 2
+    a = np.sqrt(np.abs(q))
+    safe = np.where(a == 0, 1.0, a)
+    return np.where(a == 0, 1.0, np.where(q < 0, np.sinh(safe) / safe, np.sin(safe) / safe))
+
+
+def window_gauss(x, m, dtype=np.float64):
+    """src/windowFunctions.jl:60-68 with b = m/pi."""
+    x = np.asarray(x, dtype=dtype)
+    b = dtype(m) / dtype(np.pi)
+    y = dtype(1) / np.sqrt(dtype(np.pi) * b) * np.exp(-(x * x) / b)
+    return np.where(np.abs(x) < dtype(m), y, dtype(0)).astype(dtype)
+
+
+def window_gauss_hat(n, Nt, m):
+    """src/windowFunctions.jl:70-73."""
+    n = np.asarray(n, dtype=np.float64)
+    return np.exp(-((np.pi * n / Nt) ** 2) * (m / np.pi))
+
+
+def cbspline(order, x):
+    """Cardinal B-spline of the given order on the knots 0..order (src/windowFunctions.jl:75-86),
+    the same Cox-de Boor recursion evaluated bottom-up."""
+    x = np.asarray(x)
+    dtype = x.dtype.type
+    a = [((x - j >= 0) & (x - j < 1)).astype(dtype) for j in range(order)]
+    for n in range(2, order + 1):
+        a = [((x - j) / dtype(n - 1) * a[j] + (dtype(n) - (x - j)) / dtype(n - 1) * a[j + 1]).astype(dtype)
+             for j in range(order - n + 1)]
+    return a[0]
+
+
+def window_spline(x, m, dtype=np.float64):
+    """src/windowFunctions.jl:88-95: cbspline(2m, x + m) for |x| < m."""
+    x = np.asarray(x, dtype=dtype)
+    inside = np.abs(x) < dtype(m)
+    y = cbspline(2 * m, np.where(inside, x + dtype(m), dtype(0)))
+    return np.where(inside, y, dtype(0)).astype(dtype)
+
+
+def window_spline_hat(n, Nt, m):
+    """src/windowFunctions.jl:97-99 (Julia sinc(x) = sin(pi x)/(pi x) == np.sinc)."""
+    n = np.asarray(n, dtype=np.float64)
+    return np.sinc(n / Nt) ** (2 * m)
+
+
+def window_cosh_type(x, m, sigma, dtype=np.float64):
+    """src/windowFunctions.jl:104-116."""
+    x = np.asarray(x, dtype=dtype)
+    beta = dtype(np.pi) * dtype(m) * (dtype(2) - dtype(1) / dtype(sigma))
+    inside = np.abs(x) < dtype(m)
+    alpha = np.sqrt(np.where(inside, dtype(1) - (x / dtype(m)) ** 2, dtype(1)))
+    y = dtype(1) / (np.cosh(beta) - dtype(1)) * (np.cosh(beta * alpha) - dtype(1)) / alpha
+    return np.where(inside, y, dtype(0)).astype(dtype)
+
+
+def window_cosh_type_hat(n, Nt, m, sigma):
+    """src/windowFunctions.jl:118-134."""
+    n = np.asarray(n, dtype=np.float64)
+    beta = np.pi * m * (2.0 - 1.0 / sigma)
+    gamma = beta / (2 * np.pi)
+    zeta = np.pi / (np.cosh(beta) - 1.0) * m
+    arg = m * n / Nt
+    two = 2 * np.pi * arg
+    lo = _special.i0(np.sqrt(np.maximum(beta ** 2 - two ** 2, 0.0))) - _special.j0(two)
+    hi = _special.j0(np.sqrt(np.maximum(two ** 2 - beta ** 2, 0.0))) - _special.j0(two)
+    eq = 1.0 - _special.j0(beta)
+    a = np.abs(arg)
+    return zeta * np.where(a < gamma, lo, np.where(a > gamma, hi, eq))
+
+
+def window_eval(p: "Params", x, dtype=np.float64):
+    """getWindow(window)[1] evaluated in grid units (src/windowFunctions.jl:4-19)."""
+    w = p.window
+    if w == "kaiser_bessel":
+        return window_kaiser_bessel(x, p.m, p.b, dtype)
+    if w == "kaiser_bessel_rev":
+        return window_kaiser_bessel_rev(x, p.m, p.b, dtype)
+    if w == "gauss":
+        return window_gauss(x, p.m, dtype)
+    if w == "spline":
+        return window_spline(x, p.m, dtype)
+    if w == "cosh_type":
+        return window_cosh_type(x, p.m, p.sigma, dtype)
+    raise ValueError("Window %s not yet implemented!" % w)
+
+
+def window_hat_eval(p: "Params", n, Nt):
+    """getWindow(window)[2] (always Float64)."""
+    w = p.window
+    if w == "kaiser_bessel":
+        return window_kaiser_bessel_hat(n, Nt, p.m, p.b)
+    if w == "kaiser_bessel_rev":
+        return window_kaiser_bessel_rev_hat(n, Nt, p.m, p.b)
+    if w == "gauss":
+        return window_gauss_hat(n, Nt, p.m)
+    if w == "spline":
+        return window_spline_hat(n, Nt, p.m)
+    if w == "cosh_type":
+        return window_cosh_type_hat(n, Nt, p.m, p.sigma)
+    raise ValueError("Window %s not yet implemented!" % w)
 
 
 def index_offset(N):
@@ -173,10 +299,10 @@ def window_hat_inv_lut(p: Params, cheb30=False):
         N, Nt = p.N[d], p.Nt[d]
         j = np.arange(1, N + 1, dtype=np.float64)
         if cheb30 and N > 1:
-            kap = lambda x: window_kaiser_bessel_hat(x + index_offset(N), Nt, p.m, p.b)
+            kap = lambda x: window_hat_eval(p, x + index_offset(N), Nt)
             vals = _cheb_lobatto_interp(kap, 1.0, float(N), 30, j)
         else:
-            vals = window_kaiser_bessel_hat(j + index_offset(N), Nt, p.m, p.b)
+            vals = window_hat_eval(p, j + index_offset(N), Nt)
         luts.append((1.0 / vals).astype(p.T))
     return luts
 
@@ -189,7 +315,7 @@ def precompute_lin_interp(p: Params):
     K = p.LUTSize
     step = p.m / K
     y = np.arange(K + 2, dtype=np.float64) * step
-    return window_kaiser_bessel(y, p.m, p.b, np.float64).astype(p.T)
+    return window_eval(p, y, np.float64).astype(p.T)
 
 
 def precompute_poly_interp(p: Params):
@@ -205,7 +331,7 @@ def precompute_poly_interp(p: Params):
     P = np.empty((deg, K), dtype=np.float64)
     for l in range(1, K + 1):
         y = (-(l - 0.5) + m) + t
-        samples = window_kaiser_bessel(y, m, p.b, np.float64)
+        samples = window_eval(p, y, np.float64)
         P[:, l - 1] = np.linalg.lstsq(V, samples, rcond=None)[0]
     return P.astype(p.T)
 
@@ -291,7 +417,7 @@ def _taps_blocked(ks_d, Nt_d, p: Params, tables):
     elif p.precompute == FULL:
         # exact window at the blocked coordinates: distance = (kscale - off) - l
         dist = (kscale - off.astype(T))[:, None] - taps[None, :].astype(T)
-        w = window_kaiser_bessel(dist, m, p.b, T)
+        w = window_eval(p, dist, T)
     else:
         raise ValueError("precompute mode not supported")
     return cells, w
@@ -308,6 +434,8 @@ def _taps_nonblocked(k_d, Nt_d, p: Params, tables):
     if p.precompute == FULL:
         # win((kscale-(l-1)-off)/Nt, Nt, m, sigma) in T (:131)
         x = ((kscale[:, None] - taps[None, :].astype(T)) - off[:, None].astype(T)).astype(T)
+        if p.window != "kaiser_bessel":
+            return cells, window_eval(p, x, T)
         kk = (x / T(Nt_d)).astype(T)
         m_by_N = T(m) / T(Nt_d)
         ak = np.abs(kk)
@@ -343,7 +471,7 @@ class OraclePlan:
     """Restatement of NFFTPlan (src/implementation.jl:16-141) for dims = 1:D."""
 
     def __init__(self, k, N, T=None, m=None, sigma=None, reltol=None, precompute=POLYNOMIAL,
-                 blocking=True, blockSize=None, cheb30=False):
+                 blocking=True, blockSize=None, cheb30=False, window="kaiser_bessel"):
         k = np.asarray(k)
         if k.ndim == 1:
             k = k[:, None]                                # derived.jl:23-27
@@ -352,7 +480,7 @@ class OraclePlan:
             N = (int(N),)
         if k.shape[1] != len(N):
             raise ValueError("Nodes x have dimension %d != %d" % (k.shape[1], len(N)))  # :19-21
-        self.p = init_params(N, T, m, sigma, reltol, precompute, blockSize)
+        self.p = init_params(N, T, m, sigma, reltol, precompute, blockSize, window)
         self.T = T
         self.blocking = blocking
         self.cheb30 = cheb30

@@ -87,6 +87,34 @@ def test_forward_adjoint_vs_oracle(nb, N, T, pre, kernel_mode):
         assert rel(out_fwd, O.ndft(k, f)) < 1e-7
 
 
+WINDOW_EPS = {"kaiser_bessel": 1e-7, "cosh_type": 1e-7, "gauss": 1e-3, "kaiser_bessel_rev": 1e-6, "spline": 1e-4}
+
+
+@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14)])
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("pre", [O.POLYNOMIAL, O.LINEAR, O.FULL, O.TENSOR])
+@pytest.mark.parametrize("window", ["cosh_type", "gauss", "kaiser_bessel_rev", "spline"])
+def test_other_windows_vs_oracle(nb, N, T, pre, window):
+    """the window x precompute matrix of test/accuracy.jl:41-73 (windows of src/windowFunctions.jl:41-134):
+    matched-mode parity with the oracle and the reference's per-window tolerance versus the NDFT"""
+    D, M, m = len(N), int(np.prod(N)), 5
+    k = O.random_nodes(M, D, T, seed=1)
+    p = nb.plan_nfft(k.T, N, m=m, σ=2.0, precompute=nb.PrecomputeFlags(pre), window=window)
+    assert p.params.window == window
+    po = O.OraclePlan(k, N, m=m, sigma=2.0, precompute=pre, blockSize=p.params.blockSize, window=window)
+    fHat = O.random_complex(M, T, 2)
+    f = O.random_complex(N, T, 3)
+    out_adj = p.adjoint() * fHat
+    out_fwd = p * f
+    assert rel(out_adj, po.adjoint(fHat)) < TOL[T]
+    assert rel(out_fwd, po.forward(f)) < TOL[T]
+    if T == np.float64:
+        assert rel(out_adj, O.ndft_adjoint(k, N, fHat)) < WINDOW_EPS[window]
+        assert rel(out_fwd, O.ndft(k, f)) < WINDOW_EPS[window]
+    with pytest.raises(NotImplementedError):
+        nb.plan_nfft(k.T, N, m=m, σ=2.0, window="hann")          # src/windowFunctions.jl:16
+
+
 @pytest.mark.parametrize("m", [2, 3, 4, 6, 8])
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 def test_kernel_widths_3d(nb, m, T):

@@ -21,13 +21,13 @@ def nb():
     return m
 
 
-def host_plan(nb, N, T, m, sigma, pre=4, bs=None, B=1):
+def host_plan(nb, N, T, m, sigma, pre=4, bs=None, B=1, window=0):
     L = nb.lib()
     h = C.c_void_p()
     D = len(N)
     Narr = (C.c_int64 * D)(*N)
     bsa = (C.c_int64 * D)(*bs) if bs else None
-    st = L.nfftb200_plan_create(C.byref(h), D, Narr, 0 if T == np.float32 else 1, m, sigma, 0, pre, B, bsa, -1)
+    st = L.nfftb200_plan_create(C.byref(h), D, Narr, 0 if T == np.float32 else 1, m, sigma, window, pre, B, bsa, -1)
     return st, h
 
 
@@ -105,6 +105,30 @@ def test_tables_match_oracle(nb, T, m):
     lin_o = O.precompute_lin_interp(po).astype(np.float64)
     assert lin.shape == lin_o.shape == (po.LUTSize + 2,)
     assert np.abs(lin - lin_o).max() / lin_o.max() < (1e-14 if T == np.float64 else 1e-7)
+    nb.lib().nfftb200_destroy(h)
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("wi", [1, 2, 3, 4])
+def test_other_window_tables_match_oracle(nb, T, wi):
+    """getWindow pairs other than :kaiser_bessel (src/windowFunctions.jl:41-134) through the same three tables"""
+    N, m = (40, 37), 5
+    po = O.init_params(N, T, m, 2.0, window=O.WINDOWS[wi])
+    st, h = host_plan(nb, N, T, m, 2.0, pre=4, window=wi)
+    assert st == 0
+    P = table(nb, h, 1).reshape((2 * m + 1, 2 * m), order="F")
+    Po = O.precompute_poly_interp(po).astype(np.float64)
+    t = np.linspace(-0.5, 0.5, 257)
+    V = np.vander(t, 2 * m + 1, increasing=True)
+    assert np.abs(V @ P - V @ Po).max() / np.abs(V @ Po).max() < (1e-12 if T == np.float64 else 5e-7)
+    hat = table(nb, h, 0)
+    hat_o = np.concatenate(O.window_hat_inv_lut(po)).astype(np.float64)
+    assert np.abs(hat / hat_o - 1).max() < (1e-12 if T == np.float64 else 2e-7)
+    nb.lib().nfftb200_destroy(h)
+    st, h = host_plan(nb, N, T, m, 2.0, pre=3, window=wi)
+    lin = table(nb, h, 2)
+    lin_o = O.precompute_lin_interp(po).astype(np.float64)
+    assert np.abs(lin - lin_o).max() / lin_o.max() < (1e-13 if T == np.float64 else 1e-7)
     nb.lib().nfftb200_destroy(h)
 
 

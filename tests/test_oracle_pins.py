@@ -110,6 +110,31 @@ def test_modes_agree_like_published():
     assert e < 2e-9
 
 
+WINDOW_EPS = {"kaiser_bessel": 1e-7, "cosh_type": 1e-7, "gauss": 1e-3, "kaiser_bessel_rev": 1e-6, "spline": 1e-4}
+
+
+@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14)])
+@pytest.mark.parametrize("window", ["cosh_type", "gauss", "kaiser_bessel_rev", "spline"])
+@pytest.mark.parametrize("pre,blocking", [(O.LINEAR, True), (O.FULL, False), (O.POLYNOMIAL, True)])
+def test_windows_vs_ndft_reference_tolerance(N, window, pre, blocking):
+    """test/accuracy.jl:41-73: every window of getWindow at m=5, sigma=2 against the NDFT with the reference's
+    per-window tolerance table (eps = [1e-7, 1e-7, 1e-3, 1e-6, 1e-4], test/accuracy.jl:46-47); the Chebyshev-30
+    deconvolution LUT of the reference (src/precomputation.jl:351) is used here"""
+    D, M = len(N), int(np.prod(N))
+    k = O.random_nodes(M, D, np.float64, seed=1)
+    p = O.OraclePlan(k, N, m=5, sigma=2.0, precompute=pre, blocking=blocking, window=window, cheb30=True)
+    fHat = O.random_complex(M, np.float64, 2)
+    f = O.ndft_adjoint(k, N, fHat)
+    assert rel(p.adjoint(fHat), f) < WINDOW_EPS[window]
+    assert rel(p.forward(f), O.ndft(k, f)) < WINDOW_EPS[window]
+
+
+def test_unknown_window_errors():
+    """src/windowFunctions.jl:16"""
+    with pytest.raises(ValueError):
+        O.init_params((16,), np.float64, 4, 2.0, window="hann")
+
+
 def test_window_hat_cheb30_vs_exact():
     """src/precomputation.jl:347-358: the 30-point Chebyshev interpolant equals the exact 1/phi_hat to
     <= 1e-13 relative for the BASELINE configurations (so evaluating exactly is inside the 1e-12 budget)"""
@@ -118,6 +143,11 @@ def test_window_hat_cheb30_vs_exact():
         a = np.concatenate(O.window_hat_inv_lut(p, cheb30=True))
         b = np.concatenate(O.window_hat_inv_lut(p, cheb30=False))
         assert np.abs(a / b - 1).max() < 1e-13
+    for window in O.WINDOWS[1:]:
+        p = O.init_params((255, 64), np.float64, 5, 2.0, window=window)
+        a = np.concatenate(O.window_hat_inv_lut(p, cheb30=True))
+        b = np.concatenate(O.window_hat_inv_lut(p, cheb30=False))
+        assert np.abs(a / b - 1).max() < 1e-12
 
 
 def test_sdc_known_answer():
