@@ -163,6 +163,26 @@ int nfftb200_comm_unique_id(void* out128);
 int nfftb200_partition_tiles(const int64_t* tile_start, int64_t ntiles, int nranks, int64_t* out);
 int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, int nranks, int mode);
 
+/* ---- Toeplitz (Gram) operator, the iterative-reconstruction caller either side of the path --------------
+ * nfftb200_toeplitz_kernel: calculateToeplitzKernel!(f, p, tr, fftplan) after its nodes!(p, tr)
+ * (NFFTTools/src/Toeplitz.jl:131-137, and :86-93): lambda = FFT(fftshift(adjoint(p) * ones)).  The plan's image
+ * size is 2*shape and it needs ntransforms = 1; lambda receives prod(p.N) complex values, host or device. */
+int nfftb200_toeplitz_kernel(nfftb200_plan* p, void* lambda, int where);
+
+/* convolveToeplitzKernel!(y, lambda, fftplan, ifftplan, xOS1, xOS2) (NFFTTools/src/Toeplitz.jl:230-244): the
+ * operator object owns the two cuFFT plans and the oversampled work array.  shape = size(y) (D entries),
+ * lambda has size 2*shape; ntransforms > 1 applies the same kernel to y of size (shape..., B) (batch slowest).
+ * apply overwrites y with crop(IFFT(lambda .* FFT(pad(y)))), IFFT normalised like plan_ifft. */
+typedef struct nfftb200_toeplitz nfftb200_toeplitz;
+int nfftb200_toeplitz_create(nfftb200_toeplitz** out, int D, const int64_t* shape, int dtype, int ntransforms,
+                             int device);
+int nfftb200_toeplitz_set_kernel(nfftb200_toeplitz* t, const void* lambda, int where);
+int nfftb200_toeplitz_apply(nfftb200_toeplitz* t, void* y, int where);
+int nfftb200_toeplitz_set_stream(nfftb200_toeplitz* t, void* cuda_stream);
+int nfftb200_toeplitz_sync(nfftb200_toeplitz* t);
+int nfftb200_toeplitz_destroy(nfftb200_toeplitz* t);
+const char* nfftb200_toeplitz_last_error(nfftb200_toeplitz* t);
+
 const char* nfftb200_last_error(nfftb200_plan* p);
 const char* nfftb200_status_string(int status);
 int nfftb200_version(void);

@@ -215,4 +215,51 @@ end
 Base.copy(p::B200NFFTPlan{T,D}) where {T,D} =
     B200NFFTPlan(p.k, p.N; m=p.m, σ=p.σ, precompute=p.precompute, ntransforms=p.ntransforms)
 
+# ---- Toeplitz (Gram) operator, NFFTTools/src/Toeplitz.jl ------------------------------------------------------
+"calculateToeplitzKernel!(f, p, tr, fftplan) (NFFTTools/src/Toeplitz.jl:131-137): the FFT plan lives in the library"
+function calculateToeplitzKernel!(f::AbstractArray{Complex{T},D}, p::B200NFFTPlan{T,D}, tr::Matrix{T}, fftplan=nothing) where {T,D}
+    AbstractNFFTs.nodes!(p, tr)
+    size(f) == p.N || throw(DimensionMismatch("Toeplitz kernel has size $(size(f)) != $(p.N)"))
+    check(p.handle, ccall((:nfftb200_toeplitz_kernel, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                          p.handle, pointer(f), where(f)))
+    return f
+end
+
+"calculateToeplitzKernel(shape, tr; m=4, σ=2.0, window=:kaiser_bessel) (NFFTTools/src/Toeplitz.jl:86-93)"
+function calculateToeplitzKernel(shape::NTuple{D,Int}, tr::Matrix{T}; m=4, σ=2.0, window=:kaiser_bessel, kwargs...) where {T,D}
+    p = B200NFFTPlan(tr, 2 .* shape; m, σ, window, kwargs...)
+    return calculateToeplitzKernel!(Array{Complex{T}}(undef, 2 .* shape), p, tr)
+end
+
+"owner of fftplan, ifftplan, xOS1, xOS2 and a device copy of λ for convolveToeplitzKernel! (Toeplitz.jl:230-244)"
+mutable struct ToeplitzOperator{T,D}
+    handle::Ptr{Cvoid}
+    shape::NTuple{D,Int}
+end
+
+function ToeplitzOperator(λ::AbstractArray{Complex{T},D}; ntransforms::Int=1, device::Int=0) where {T,D}
+    shape = size(λ) .÷ 2
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:nfftb200_toeplitz_create, libnfftb200), Cint,
+                        (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cint),
+                        h, D, collect(Int64, shape), dtype_code(T), ntransforms, device))
+    op = ToeplitzOperator{T,D}(h[], shape)
+    finalizer(op) do q
+        q.handle == C_NULL || ccall((:nfftb200_toeplitz_destroy, libnfftb200), Cint, (Ptr{Cvoid},), q.handle)
+        q.handle = C_NULL
+    end
+    check(C_NULL, ccall((:nfftb200_toeplitz_set_kernel, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                        op.handle, pointer(λ), where(λ)))
+    return op
+end
+
+"convolveToeplitzKernel!(y, λ) with the plans and work arrays held by `op`"
+function convolveToeplitzKernel!(y::AbstractArray{Complex{T}}, op::ToeplitzOperator{T}) where {T}
+    check(C_NULL, ccall((:nfftb200_toeplitz_apply, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                        op.handle, pointer(y), where(y)))
+    return y
+end
+convolveToeplitzKernel!(y::AbstractArray{Complex{T},D}, λ::AbstractArray{Complex{T},D}) where {T,D} =
+    convolveToeplitzKernel!(y, ToeplitzOperator(λ))
+
 end # module

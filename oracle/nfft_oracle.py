@@ -669,6 +669,42 @@ def sdc(plan: OraclePlan, iters=20):
 
 
 # --------------------------------------------------------------------------------------
+# Toeplitz (Gram) operator  (NFFTTools/src/Toeplitz.jl)
+# --------------------------------------------------------------------------------------
+def calculate_toeplitz_kernel(shape, k, m=4, sigma=2.0, window="kaiser_bessel", precompute=POLYNOMIAL):
+    """calculateToeplitzKernel (NFFTTools/src/Toeplitz.jl:86-93): adjoint NFFT of ones on the 2x oversampled
+    image grid, fftshift, unnormalised forward FFT.  k: (M, D)."""
+    k = np.asarray(k)
+    shape_os = tuple(2 * int(s) for s in shape)
+    p = OraclePlan(k, shape_os, m=m, sigma=sigma, window=window, precompute=precompute)
+    cT = np.complex64 if p.T == np.float32 else np.complex128
+    eig = p.adjoint(np.ones(k.shape[0], dtype=cT))
+    return np.asfortranarray(_sfft.fftn(np.fft.fftshift(eig)).astype(cT))
+
+
+def calculate_toeplitz_kernel_explicit(shape, k):
+    """calculateToeplitzKernel_explicit / getMatrixElement (NFFTTools/src/Toeplitz.jl:145-168):
+    lambda[i] = sum_j exp(-2 pi i k_j . (shape_os/2 - i)), i 0-based, then fftshift and FFT."""
+    k = np.asarray(k)
+    shape_os = tuple(2 * int(s) for s in shape)
+    cT = np.complex64 if k.dtype == np.float32 else np.complex128
+    lam = ndft_adjoint(k.astype(np.float64), shape_os, np.ones(k.shape[0], dtype=np.complex128))
+    return np.asfortranarray(_sfft.fftn(np.fft.fftshift(lam)).astype(cT))
+
+
+def convolve_toeplitz_kernel(y, lam):
+    """convolveToeplitzKernel! (NFFTTools/src/Toeplitz.jl:230-244): zero-pad, FFT, multiply, normalised IFFT,
+    crop.  Returns the new y (same dtype)."""
+    y = np.asarray(y)
+    x = np.zeros(lam.shape, dtype=lam.dtype, order="F")
+    sl = tuple(slice(0, n) for n in y.shape)
+    x[sl] = y
+    x = _sfft.fftn(x).astype(lam.dtype) * lam
+    x = _sfft.ifftn(x).astype(lam.dtype)
+    return np.asfortranarray(x[sl].astype(y.dtype))
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8d)
 # --------------------------------------------------------------------------------------
 def random_nodes(M, D, T, seed=1):

@@ -490,3 +490,71 @@ def test_multi_gpu_node_and_batch_sharding():
                           "--master-addr", "127.0.0.1", "--master-port", "29561",
                           _os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert "MGPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def _approx(a, b, rtol):
+    """Julia's isapprox on arrays: norm(a-b) <= rtol * max(norm(a), norm(b))"""
+    a = np.asarray(a).ravel().astype(np.complex128)
+    b = np.asarray(b).ravel().astype(np.complex128)
+    return np.linalg.norm(a - b) <= rtol * max(np.linalg.norm(a), np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("shape,T,M", [((32, 32), np.float64, 1000), ((33, 33), np.float64, 1000),
+                                       ((32, 33), np.float32, 1000), ((32, 32, 32), np.float32, 1000),
+                                       ((100,), np.float64, 500)])
+def test_toeplitz_kernel(nb, shape, T, M):
+    """test/testToeplitz.jl:10-44,67-87: calculateToeplitzKernel / calculateToeplitzKernel! vs the explicit kernel
+    (rtol 1e-6 F64 / 1e-5 F32) and vs the oracle's restatement of NFFTTools/src/Toeplitz.jl:86-93"""
+    D = len(shape)
+    k = O.random_nodes(M, D, T, seed=21)
+    cT = np.complex64 if T == np.float32 else np.complex128
+    Ka = nb.calculateToeplitzKernel(shape, k.T, m=4, σ=2.0)
+    assert Ka.dtype == cT and Ka.shape == tuple(2 * s for s in shape)
+    rt = 1e-6 if T == np.float64 else 1e-5
+    assert _approx(Ka, O.calculate_toeplitz_kernel_explicit(shape, k), rt)
+    assert rel(Ka, O.calculate_toeplitz_kernel(shape, k, m=4, sigma=2.0)) < (1e-11 if T == np.float64 else 2e-5)
+    # the less-allocating constructor: an existing plan with other nodes, re-noded in place
+    p = nb.plan_nfft(O.random_nodes(77, D, T, seed=22).T, tuple(2 * s for s in shape), m=4, σ=2.0)
+    Kb = np.empty(tuple(2 * s for s in shape), dtype=cT, order="F")
+    assert nb.calculateToeplitzKernel_(Kb, p, k.T) is Kb
+    assert np.array_equal(Ka, Kb)
+    with pytest.raises(nb.DimensionMismatch):
+        nb.calculateToeplitzKernel_(np.empty(shape, dtype=cT, order="F"), p, k.T)
+
+
+def test_toeplitz_convolve(nb):
+    """test/testToeplitz.jl:47-58: convolveToeplitzKernel!(x, K) == nfft_adjoint(trj, N, nfft(trj, x)), rtol 1e-5,
+    host and device buffers, one-shot and pre-planned (batched) operator"""
+    import torch
+    Nx, T = 32, np.float32
+    k = O.random_nodes(10000, 2, T, seed=23)
+    Ka = nb.calculateToeplitzKernel((Nx, Nx), k.T, m=4, σ=2.0)
+    x = O.random_complex((Nx, Nx), T, 24)
+    xN = nb.nfft_adjoint(k.T, (Nx, Nx), nb.nfft(k.T, x))
+    y = x.copy(order="F")
+    assert nb.convolveToeplitzKernel_(y, Ka) is y
+    assert _approx(y, xN, 1e-5)
+    assert rel(y, O.convolve_toeplitz_kernel(x, Ka)) < 1e-5
+    # device buffers + operator re-use, batch of 3 images
+    kd = torch.from_numpy(np.ascontiguousarray(k)).cuda().T
+    Kd = nb.calculateToeplitzKernel((Nx, Nx), kd, m=4, σ=2.0)
+    assert Kd.is_cuda and rel(Kd.cpu().numpy(), Ka) < 1e-6
+    op = nb.ToeplitzOperator(Kd, ntransforms=3)
+    xb = np.stack([O.random_complex((Nx, Nx), T, 30 + i) for i in range(3)], axis=-1)
+    yb = torch.empty((3, Nx, Nx), dtype=torch.complex64, device="cuda").permute(2, 1, 0)
+    yb.copy_(torch.from_numpy(xb))
+    for _ in range(2):                                    # applying twice == applying the Gram operator twice
+        op.apply_(yb)
+    ref = np.stack([O.convolve_toeplitz_kernel(O.convolve_toeplitz_kernel(xb[..., i], Ka), Ka) for i in range(3)], axis=-1)
+    assert rel(yb.cpu().numpy(), ref) < 2e-5
+    with pytest.raises(nb.DimensionMismatch):
+        op.apply_(y)
+    # Float64, 3-D, rectangular
+    k3 = O.random_nodes(3000, 3, np.float64, seed=25)
+    K3 = nb.calculateToeplitzKernel((12, 10, 9), k3.T, m=6, σ=2.0)
+    x3 = O.random_complex((12, 10, 9), np.float64, 26)
+    p3 = nb.plan_nfft(k3.T, (12, 10, 9), m=6, σ=2.0)
+    y3 = x3.copy(order="F")
+    nb.convolveToeplitzKernel_(y3, K3)
+    assert rel(y3, p3.adjoint() * (p3 * x3)) < 1e-9
+    assert rel(y3, O.convolve_toeplitz_kernel(x3, K3)) < 1e-12

@@ -129,6 +129,42 @@ def test_windows_vs_ndft_reference_tolerance(N, window, pre, blocking):
     assert rel(p.forward(f), O.ndft(k, f)) < WINDOW_EPS[window]
 
 
+def _approx(a, b, rtol):
+    """Julia's isapprox on arrays: norm(a-b) <= rtol * max(norm(a), norm(b))"""
+    a = np.asarray(a).ravel().astype(np.complex128)
+    b = np.asarray(b).ravel().astype(np.complex128)
+    return np.linalg.norm(a - b) <= rtol * max(np.linalg.norm(a), np.linalg.norm(b))
+
+
+def test_toeplitz_kernel_matches_explicit():
+    """test/testToeplitz.jl:10-33,36-44,67-87: NFFT-based Toeplitz kernel vs the explicit one, rtol 1e-6 (F64) /
+    1e-5 (F32), square, rectangular and 3-D"""
+    rng = np.random.default_rng(5)
+    for Nx in (32, 33):
+        k = rng.random((1000, 2)) - 0.5
+        Ka = O.calculate_toeplitz_kernel((Nx, Nx), k, m=4, sigma=2.0)
+        assert Ka.dtype == np.complex128 and Ka.shape == (2 * Nx, 2 * Nx)
+        assert _approx(Ka, O.calculate_toeplitz_kernel_explicit((Nx, Nx), k), 1e-6)
+    k = (rng.random((1000, 2)) - 0.5).astype(np.float32)
+    Ka = O.calculate_toeplitz_kernel((32, 33), k, m=4, sigma=2.0)
+    assert Ka.dtype == np.complex64 and Ka.shape == (64, 66)
+    assert _approx(Ka, O.calculate_toeplitz_kernel_explicit((32, 33), k), 1e-5)
+    k = (rng.random((1000, 3)) - 0.5).astype(np.float32)
+    assert _approx(O.calculate_toeplitz_kernel((16, 16, 16), k), O.calculate_toeplitz_kernel_explicit((16, 16, 16), k), 1e-5)
+
+
+def test_toeplitz_convolve_equals_gram():
+    """test/testToeplitz.jl:47-58: convolveToeplitzKernel!(x, K) == nfft_adjoint(nfft(x)), rtol 1e-5 (F32)"""
+    rng = np.random.default_rng(6)
+    Nx = 32
+    k = (rng.random((10000, 2)) - 0.5).astype(np.float32)
+    Ka = O.calculate_toeplitz_kernel((Nx, Nx), k, m=4, sigma=2.0)
+    x = O.random_complex((Nx, Nx), np.float32, 7)
+    p = O.OraclePlan(k, (Nx, Nx))                      # nfft/nfft_adjoint defaults: reltol 1e-9 -> m=5
+    xN = p.adjoint(p.forward(x))
+    assert _approx(O.convolve_toeplitz_kernel(x, Ka), xN, 1e-5)
+
+
 def test_unknown_window_errors():
     """src/windowFunctions.jl:16"""
     with pytest.raises(ValueError):
