@@ -517,7 +517,7 @@ def test_toeplitz_kernel(nb, shape, T, M):
     p = nb.plan_nfft(O.random_nodes(77, D, T, seed=22).T, tuple(2 * s for s in shape), m=4, σ=2.0)
     Kb = np.empty(tuple(2 * s for s in shape), dtype=cT, order="F")
     assert nb.calculateToeplitzKernel_(Kb, p, k.T) is Kb
-    assert np.array_equal(Ka, Kb)
+    assert rel(Kb, Ka) < (1e-13 if T == np.float64 else 1e-6)    # work-item split may differ after nodes!
     with pytest.raises(nb.DimensionMismatch):
         nb.calculateToeplitzKernel_(np.empty(shape, dtype=cT, order="F"), p, k.T)
 
