@@ -141,7 +141,10 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
  *   1 = force the generic warp-per-node kernels (global vector REDs),
  *   2 = tiled spreader with the halo flushed by vector REDs instead of scratch + gather,
  *   3 = auto, but the interpolator never uses the TMA tensor-map load,
- *   4 = auto, but the full (unpruned) cuFFT plan. */
+ *   4 = auto, but the full (unpruned) cuFFT plan,
+ *   5 = auto, but the per-cell form of the gather pass,
+ *   6 = node-sharded plans: NCCL reduce-scatter of full-grid replicas instead of the fused spread + slab gather
+ *       over peer memory (the baseline the fused path is measured against). */
 int nfftb200_set_kernel_mode(nfftb200_plan* p, int mode);
 /* number of kernels + library calls this plan has launched so far */
 int nfftb200_get_launch_count(nfftb200_plan* p, int64_t* n);
@@ -156,12 +159,17 @@ int nfftb200_sync(nfftb200_plan* p);
  * NFFTB200_SHARD_BATCH (each rank owns ntransforms/nranks transforms, no exec collective)
  * or NFFTB200_SHARD_NODES (each rank owns a node range; adjoint = local spread ->
  * ncclReduceScatter over slabs of the last grid dim -> slab FFT; forward = slab FFT ->
- * ncclAllGather -> local interpolation). */
+ * ncclAllGather -> local interpolation).  Where it applies (see nfftb200_comm_is_fused) the adjoint's spread and
+ * reduce-scatter are one fused step over peer memory: every rank's per-tile scratch is exported with CUDA IPC and
+ * each rank gathers its slab straight from the owners of the covering tiles. */
 int nfftb200_comm_unique_id(void* out128);
 /* host logic of the node sharding: tile-aligned cut of the sorted node list into nranks ranges of ~M/nranks
  * nodes; tile_start has ntiles+1 prefix sums, out receives nranks+1 tile boundaries */
 int nfftb200_partition_tiles(const int64_t* tile_start, int64_t ntiles, int nranks, int64_t* out);
 int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, int nranks, int mode);
+/* 1 if the node-sharded adjoint of this plan runs the fused spread + slab gather over peer memory (3-D tiled
+ * plans whose slabs are whole tile layers, <= 8 ranks, CUDA IPC available), 0 if it uses ncclReduceScatter */
+int nfftb200_comm_is_fused(nfftb200_plan* p);
 
 /* ---- Toeplitz (Gram) operator, the iterative-reconstruction caller either side of the path --------------
  * nfftb200_toeplitz_kernel: calculateToeplitzKernel!(f, p, tr, fftplan) after its nodes!(p, tr)

@@ -13,6 +13,12 @@
 //     forward : apodise/zero-pad on the transposed slabs -> FFT over dim D -> all-to-all back -> local FFT
 //               over dims 1..D-1 -> ncclAllGather ("broadcast the grid") -> interpolate the own node range
 //     For D == 1 (and when the grid does not divide) the FFT is replicated after an all-gather.
+//  Fused spread + reduce-scatter over peer memory (3-D, default when it applies; kernel mode 6 selects the NCCL
+//  reduce-scatter baseline): every rank spreads its tile range into a per-tile scratch that is exported with
+//  CUDA IPC; after one stream-ordered barrier each rank's gather pass builds ITS z-slab directly, reading the
+//  tiles that cover it from whichever rank owns them (P2P loads over NVLink).  Only the tiles straddling a slab
+//  boundary cross the link instead of (P-1)/P of the grid, nothing is atomically added, the full-grid replica is
+//  never written, and the summation order is fixed.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -75,6 +81,18 @@ struct CommState {
     void* d_a = nullptr;      // z-slab / transposed slab work buffer  (gsz/P complex)
     void* d_b = nullptr;      // pack / unpack buffer                  (gsz/P complex)
     int64_t inner = 1, mid = 1, outer = 1, Ms = 1, Os = 1;
+    // fused spread + reduce-scatter over peer memory
+    bool fused = false;
+    void* d_peerbuf = nullptr; int64_t cap_peerbuf = 0;   // own tile scratch (IPC-exported)
+    void* peer_ptr[NFFTB_MAX_PEERS] = {};                 // mappings of the other ranks' scratch
+    PeerTab tab{};
+    void* d_xchg = nullptr;                               // handle exchange / barrier word
+};
+
+struct PeerMsg {
+    cudaIpcMemHandle_t h;
+    int ok;
+    int pad;
 };
 
 CommState* cs(nfftb200_plan* p) { return reinterpret_cast<CommState*>(p->nccl_comm); }
@@ -192,6 +210,10 @@ void nfftb_comm_destroy(nfftb200_plan* p)
     if (c->have_last) cufftDestroy(c->fft_last);
     if (c->d_a) cudaFree(c->d_a);
     if (c->d_b) cudaFree(c->d_b);
+    for (int r = 0; r < NFFTB_MAX_PEERS; r++)
+        if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
+    if (c->d_peerbuf) cudaFree(c->d_peerbuf);
+    if (c->d_xchg) cudaFree(c->d_xchg);
     if (c->comm && api().ok) api().CommDestroy(c->comm);
     delete c;
     p->nccl_comm = nullptr;
@@ -202,6 +224,71 @@ static void own_tiles(nfftb200_plan* p, int64_t& t_lo, int64_t& t_hi)
     std::vector<int64_t> ts(p->h_tile_start.begin(), p->h_tile_start.end()), cut((size_t)p->nranks + 1);
     nfftb200_partition_tiles(ts.data(), p->ntiles, p->nranks, cut.data());
     t_lo = cut[(size_t)p->rank]; t_hi = cut[(size_t)p->rank + 1];
+}
+
+// Collective (every rank calls it from nodes!): size the own tile scratch for the new node set, export it and map
+// the scratch of all other ranks.  Any rank that cannot take part switches the whole group to the NCCL path.
+int nfftb_comm_after_nodes(nfftb200_plan* p)
+{
+    CommState* c = cs(p);
+    if (!c || !c->comm || p->shard_mode != NFFTB200_SHARD_NODES) return NFFTB200_OK;
+    const int P = p->nranks;
+    c->fused = false;
+    if (P > NFFTB_MAX_PEERS) return NFFTB200_OK;                          // same decision on every rank
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    for (int r = 0; r < NFFTB_MAX_PEERS; r++)
+        if (c->peer_ptr[r]) { cudaIpcCloseMemHandle(c->peer_ptr[r]); c->peer_ptr[r] = nullptr; }
+    if (!c->d_xchg) CUDA_TRY(p, cudaMalloc(&c->d_xchg, sizeof(PeerMsg) * NFFTB_MAX_PEERS));
+    std::vector<PeerMsg> msg((size_t)P);
+    auto exchange = [&](const PeerMsg& mine) -> int {                     // all-gather of one PeerMsg per rank
+        CUDA_TRY(p, cudaMemcpyAsync((char*)c->d_xchg + sizeof(PeerMsg) * p->rank, &mine, sizeof(PeerMsg), cudaMemcpyHostToDevice, p->stream));
+        NCCL_TRY(p, api().AllGather((char*)c->d_xchg + sizeof(PeerMsg) * p->rank, c->d_xchg, sizeof(PeerMsg), ncclChar, c->comm, p->stream));
+        CUDA_TRY(p, cudaMemcpyAsync(msg.data(), c->d_xchg, sizeof(PeerMsg) * P, cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        return NFFTB200_OK;
+    };
+    PeerMsg mine{};
+    // round 1: everyone has closed its mappings (so buffers may be re-allocated) and says whether the path applies
+    const int PN = nfftb_peer_tile_cells(p);
+    mine.ok = (PN > 0 && c->slab && c->Os % 16 == 0) ? 1 : 0;
+    ST_TRY(exchange(mine));
+    bool all = true;
+    for (int r = 0; r < P; r++) all = all && msg[(size_t)r].ok;
+    if (!all) return NFFTB200_OK;
+    // round 2: allocate, export
+    std::vector<int64_t> ts(p->h_tile_start.begin(), p->h_tile_start.end()), cut((size_t)P + 1);
+    nfftb200_partition_tiles(ts.data(), p->ntiles, P, cut.data());
+    c->tab.n = P;
+    for (int r = 0; r <= P; r++) c->tab.cut[r] = (int)cut[(size_t)r];
+    for (int r = 0; r < P; r++) c->tab.item_lo[r] = p->h_tile_items[(size_t)cut[(size_t)r]];
+    const int64_t items = p->h_tile_items[(size_t)cut[(size_t)p->rank + 1]] - p->h_tile_items[(size_t)cut[(size_t)p->rank]];
+    const int64_t need = std::max<int64_t>(items, 1) * PN * 2 * (int64_t)p->esz();
+    mine.ok = 1;
+    if (need > c->cap_peerbuf) {
+        if (c->d_peerbuf) cudaFree(c->d_peerbuf);
+        c->d_peerbuf = nullptr; c->cap_peerbuf = 0;
+        if (cudaMalloc(&c->d_peerbuf, (size_t)need) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+        else c->cap_peerbuf = need;
+    }
+    if (mine.ok && cudaIpcGetMemHandle(&mine.h, c->d_peerbuf) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    ST_TRY(exchange(mine));
+    for (int r = 0; r < P; r++) all = all && msg[(size_t)r].ok;
+    if (!all) return NFFTB200_OK;
+    // round 3: map, agree
+    const std::vector<PeerMsg> handles = msg;
+    mine.ok = 1;
+    for (int r = 0; r < P && mine.ok; r++) {
+        if (r == p->rank) continue;
+        if (cudaIpcOpenMemHandle(&c->peer_ptr[r], handles[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError(); c->peer_ptr[r] = nullptr; mine.ok = 0;
+        }
+    }
+    ST_TRY(exchange(mine));
+    for (int r = 0; r < P; r++) all = all && msg[(size_t)r].ok;
+    if (!all) return NFFTB200_OK;
+    for (int r = 0; r < P; r++) c->tab.base[r] = r == p->rank ? c->d_peerbuf : c->peer_ptr[r];
+    c->fused = true;
+    return NFFTB200_OK;
 }
 
 int nfftb_slab_deconvolve(nfftb200_plan* p, const void* d_f, void* d_slab, int64_t mid_off, int64_t Ms);            // deconv.cu
@@ -217,12 +304,23 @@ int nfftb_comm_exec_adjoint(nfftb200_plan* p, const void* d_fhat, void* d_f)
     int64_t t_lo, t_hi;
     own_tiles(p, t_lo, t_hi);
     if (p->timing) cudaEventRecord(p->ev[0], p->stream);
-    ST_TRY(nfftb_spread(p, d_fhat, p->d_grid, 1, 1, t_lo, t_hi));
+    const bool fused = c->fused && c->slab && p->kernel_mode != 6 && p->kernel_mode != 1 && p->kernel_mode != 2;
+    if (fused) {
+        // spread the own tiles into the exported scratch; the barrier orders every rank's spread before any gather
+        ST_TRY(nfftb_peer_spread(p, d_fhat, c->d_peerbuf, t_lo, t_hi));
+        NCCL_TRY(p, api().AllReduce(c->d_xchg, c->d_xchg, 1, ncclFloat, ncclSum, c->comm, p->stream));
+        ST_TRY(nfftb_peer_gather(p, c->d_a, (int)(p->rank * c->Os / 16), (int)(c->Os / 16), c->tab));
+        p->launches++;
+    } else {
+        ST_TRY(nfftb_spread(p, d_fhat, p->d_grid, 1, 1, t_lo, t_hi));
+    }
     if (p->timing) cudaEventRecord(p->ev[1], p->stream);
     if (c->slab) {
-        // reduce-scatter over slabs of the slowest grid dimension
-        NCCL_TRY(p, api().ReduceScatter(p->d_grid, c->d_a, slab_reals, nccl_real(p), ncclSum, c->comm, p->stream));
-        p->launches++;
+        if (!fused) {
+            // reduce-scatter over slabs of the slowest grid dimension
+            NCCL_TRY(p, api().ReduceScatter(p->d_grid, c->d_a, slab_reals, nccl_real(p), ncclSum, c->comm, p->stream));
+            p->launches++;
+        }
         ST_TRY(exec_fft(p, c->fft_local, c->d_a, +1));
         const long long n = p->gsz / P;
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 32);
@@ -297,6 +395,12 @@ int nfftb200_comm_unique_id(void* out128)
     return NFFTB200_OK;
 }
 
+int nfftb200_comm_is_fused(nfftb200_plan* p)
+{
+    CommState* c = p ? cs(p) : nullptr;
+    return (c && c->fused && p->shard_mode == NFFTB200_SHARD_NODES) ? 1 : 0;
+}
+
 int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, int nranks, int mode)
 {
     if (!p) return NFFTB200_BAD_ARGUMENT;
@@ -323,10 +427,12 @@ int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, i
     p->rank = rank; p->nranks = nranks;
     NCCL_TRY(p, api().CommInitRank(&c->comm, nranks, id, rank));
     int st = setup_slab(p);
+    if (st == NFFTB200_OK) {
+        p->shard_mode = NFFTB200_SHARD_NODES;
+        if (p->have_nodes) st = nfftb_comm_after_nodes(p);
+    }
     if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
-    if (st != NFFTB200_OK) return st;
-    p->shard_mode = NFFTB200_SHARD_NODES;
-    return NFFTB200_OK;
+    return st;
 }
 
 }  // extern "C"

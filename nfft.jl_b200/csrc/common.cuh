@@ -50,6 +50,15 @@ struct GeomDev {
     long long fsz;            // prod(N)
 };
 
+// tile scratch of every rank as seen from this process (node sharding over peer memory, comm.cu / spread.cu)
+#define NFFTB_MAX_PEERS 8
+struct PeerTab {
+    const void* base[NFFTB_MAX_PEERS];   // rank r's scratch (own pointer or CUDA-IPC mapping)
+    int cut[NFFTB_MAX_PEERS + 1];        // rank r owns tiles [cut[r], cut[r+1])
+    int item_lo[NFFTB_MAX_PEERS];        // first work item of rank r (scratch slot 0)
+    int n;                               // ranks
+};
+
 // ---------------------------------------------------------------------------------------
 // the plan (host side)
 // ---------------------------------------------------------------------------------------
@@ -215,6 +224,10 @@ int nfftb_interp(nfftb200_plan* p, const void* d_g, void* d_fhat, int B, int is_
                  int64_t t_lo, int64_t t_hi);                                   // interp.cu
 int nfftb_build_tables(nfftb200_plan* p);
 size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs);                // spread.cu
+int nfftb_peer_tile_cells(nfftb200_plan* p);                                     // spread.cu (node sharding over peer memory)
+int nfftb_peer_spread(nfftb200_plan* p, const void* d_fhat, void* d_scratch, int64_t t_lo, int64_t t_hi);
+int nfftb_peer_gather(nfftb200_plan* p, void* d_slab, int layer_lo, int nlayers, const PeerTab& pt);
+int nfftb_comm_after_nodes(nfftb200_plan* p);                                    // comm.cu
 int nfftb_spread_2d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi);                    // twod.cu
 int nfftb_interp_2d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi);
 int nfftb_spread_1d(nfftb200_plan* p, const void* fhat, void* g, int B, int is_complex, int t_lo, int t_hi);   // oned.cu

@@ -413,6 +413,8 @@ int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     if (p->timing) { float ms = 0; cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->t[0] = ms * 1e-3; }
     p->have_nodes = true;
+    // node sharding: (re)size and re-export the tile scratch for the new node set -- collective over the ranks
+    if (p->shard_mode == NFFTB200_SHARD_NODES) ST_TRY(nfftb_comm_after_nodes(p));
     return NFFTB200_OK;
 }
 

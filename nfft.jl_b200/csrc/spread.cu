@@ -497,10 +497,15 @@ k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cp
 // ALL z of one tile layer, so the x/y candidate search and the work-item lookups are done once per 16 output
 // cells and the accumulators stay in registers; the z halos of the layers below/above are added with compile-time
 // z ranges.  ~16x fewer instructions per output cell than the per-cell kernel.
-template <typename T, int MT, int BSZ>
+// PEER = true is the multi-GPU form (node sharding, comm.cu): the tile scratch of every rank is mapped into this
+// process (CUDA IPC over NVLink), a tile's sub-grid is read from the rank that owns the tile, and only the z layers
+// [tz0, tz0 + gridDim.z) of this rank's slab are produced -- the spread's halo exchange and the reduce-scatter
+// in one pass, with no atomics and a fixed summation order.
+template <typename T, int MT, int BSZ, bool PEER>
 __global__ void __launch_bounds__(128)
 k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cplx<T>::type* __restrict__ g,
-                const int32_t* __restrict__ tile_items, int tile_lo, int tile_hi, int item_lo, int item_hi, GeomDev geo)
+                const int32_t* __restrict__ tile_items, int tile_lo, int tile_hi, int item_lo, int item_hi, GeomDev geo,
+                const __grid_constant__ PeerTab pt, int tz0)
 {
     using C = typename Cplx<T>::type;
     constexpr int L = 2 * MT;
@@ -509,9 +514,11 @@ k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cpl
     const int plane = PX * PY;
     const unsigned PN = (unsigned)plane * PZ;
     const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    const int u1 = blockIdx.y, tzc = blockIdx.z % geo.nb[2], b = blockIdx.z / geo.nb[2];
+    const int u1 = blockIdx.y;
+    const int tzc = PEER ? (int)blockIdx.z + tz0 : (int)(blockIdx.z % geo.nb[2]);
+    const int b = PEER ? 0 : (int)(blockIdx.z / geo.nb[2]);
     if (u0 >= geo.Nt[0]) return;
-    scratch += (size_t)b * (size_t)(item_hi - item_lo) * PN;
+    if (!PEER) scratch += (size_t)b * (size_t)(item_hi - item_lo) * PN;
     auto cover = [&](int u, int d, int tmul, int pmul, int (&tt)[3], int (&po)[3]) -> int {
         const int bs = geo.bs[d], nb = geo.nb[d], Nt = geo.Nt[d];
         const int t = (int)fastdiv((unsigned)u, geo.inv_bs[d]), l = u - t * bs;
@@ -552,10 +559,17 @@ k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cpl
             auto add_layer = [&](int tzl, auto lo_tag, auto cnt_tag, int pz0) {
                 constexpr int LO = decltype(lo_tag)::value, CNT = decltype(cnt_tag)::value;
                 const int tile = tzl * tmz + txy;
-                if (tile < tile_lo || tile >= tile_hi) return;
+                const C* sbase = scratch;
+                int ilo = item_lo;
+                if (PEER) {
+                    int r = 0;
+                    while (r + 1 < pt.n && tile >= pt.cut[r + 1]) r++;       // owner of the tile
+                    sbase = (const C*)pt.base[r];
+                    ilo = pt.item_lo[r];
+                } else if (tile < tile_lo || tile >= tile_hi) return;
                 const int ia = tile_items[tile], ib = tile_items[tile + 1];
                 for (int it = ia; it < ib; it++) {
-                    const C* sp = scratch + ((long long)(it - item_lo) * (long long)PN + (long long)pz0 * plane + oxy);
+                    const C* sp = sbase + ((long long)(it - ilo) * (long long)PN + (long long)pz0 * plane + oxy);
 #pragma unroll
                     for (int k = 0; k < CNT; k++) {
                         if (w0) { const C c = sp[(size_t)k * plane]; ax0[LO + k] += c.x; ay0[LO + k] += c.y; }
@@ -567,7 +581,7 @@ k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cpl
             add_layer(tzp, std::integral_constant<int, 0>{}, std::integral_constant<int, MT>{}, MT + BSZ);
             add_layer(tzn, std::integral_constant<int, BSZ - MT>{}, std::integral_constant<int, MT>{}, 0);
         }
-    C* dst = g + (size_t)b * geo.gsz + ((size_t)(tzc * BSZ) * geo.Nt[1] + u1) * geo.Nt[0] + u0;
+    C* dst = g + (size_t)b * geo.gsz + ((size_t)((tzc - (PEER ? tz0 : 0)) * BSZ) * geo.Nt[1] + u1) * geo.Nt[0] + u0;
     const size_t gplane = (size_t)geo.Nt[0] * geo.Nt[1];
 #pragma unroll
     for (int k = 0; k < BSZ; k++) {
@@ -624,7 +638,7 @@ int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_l
         if (p->kernel_mode != 5 && geo.bs[2] == 16 && geo.Nt[2] % 16 == 0 && 16 >= 2 * MT) {
             while (bx < 128 && bx < units) bx <<= 1;
             dim3 gc((units + bx - 1) / bx, geo.Nt[1], geo.nb[2] * B);
-            k_gather_cols3d<T, MT, 16><<<gc, bx, 0, st>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo);
+            k_gather_cols3d<T, MT, 16, false><<<gc, bx, 0, st>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo, PeerTab{}, 0);
             p->launches += 2;
             CUDA_TRY(p, cudaGetLastError());
             return NFFTB200_OK;
@@ -644,6 +658,58 @@ int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_l
                                                 p->d_items, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
         p->launches += 2;
     }
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
+// ---- node sharding over peer memory (comm.cu): spread the own tile range into an IPC-exported scratch, then
+// gather the own z-slab from every rank's scratch
+template <typename T, int MT>
+int peer_cells(nfftb200_plan* p)
+{
+    GeomDev geo = make_geom<T>(p);
+    SubLayout<T, MT, 8> lay(geo.bs);
+    if (lay.bytes() > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return 0;
+    if (geo.bs[2] != 16 || geo.Nt[2] % 16 != 0 || 16 < 2 * MT) return 0;
+    for (int d = 0; d < 3; d++) {
+        const int last = geo.Nt[d] - (geo.nb[d] - 1) * geo.bs[d];
+        if (geo.bs[d] < MT || last < MT) return 0;
+        if (d == 0 && ((geo.bs[0] & 1) || (last & 1))) return 0;
+    }
+    return (geo.bs[0] + 2 * MT) * (geo.bs[1] + 2 * MT) * (geo.bs[2] + 2 * MT);
+}
+
+template <typename T, int MT>
+int peer_spread(nfftb200_plan* p, const void* fhat, void* scratch, int t_lo, int t_hi)
+{
+    using C = typename Cplx<T>::type;
+    GeomDev geo = make_geom<T>(p);
+    SubLayout<T, MT, 8> lay(geo.bs);
+    const size_t smem = lay.bytes();
+    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
+    if (item_hi == item_lo) return NFFTB200_OK;
+    if (p->timing) { cudaEventRecord(p->evk[0], p->stream); cudaEventRecord(p->evk[1], p->stream); }
+    auto kern = k_spread_sub3d<T, MT, true, 8>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(item_hi - item_lo, 1), 256, smem, p->stream>>>((const C*)fhat, nullptr, (C*)scratch, (const T*)p->d_xs, p->d_perm,
+                                                               p->d_items, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
+    if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; }
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
+template <typename T, int MT>
+int peer_gather(nfftb200_plan* p, void* slab, int layer_lo, int nlayers, const PeerTab& pt)
+{
+    using C = typename Cplx<T>::type;
+    GeomDev geo = make_geom<T>(p);
+    const int units = geo.Nt[0] / 2;
+    int bx = 32;
+    while (bx < 128 && bx < units) bx <<= 1;
+    dim3 gc((units + bx - 1) / bx, geo.Nt[1], nlayers);
+    k_gather_cols3d<T, MT, 16, true><<<gc, bx, 0, p->stream>>>(nullptr, (C*)slab, p->d_tile_items, 0, 0, 0, 0, geo, pt, layer_lo);
+    p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;
 }
@@ -730,6 +796,36 @@ size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs)
         default: return 0;
     }
 #undef CASE_M
+}
+
+#define PEER_DISPATCH(FN, ...)                                                                     \
+    switch (p->m) {                                                                                \
+        case 2: return p->dtype == NFFTB200_F32 ? FN<float, 2>(__VA_ARGS__) : FN<double, 2>(__VA_ARGS__); \
+        case 3: return p->dtype == NFFTB200_F32 ? FN<float, 3>(__VA_ARGS__) : FN<double, 3>(__VA_ARGS__); \
+        case 4: return p->dtype == NFFTB200_F32 ? FN<float, 4>(__VA_ARGS__) : FN<double, 4>(__VA_ARGS__); \
+        case 5: return p->dtype == NFFTB200_F32 ? FN<float, 5>(__VA_ARGS__) : FN<double, 5>(__VA_ARGS__); \
+        case 6: return p->dtype == NFFTB200_F32 ? FN<float, 6>(__VA_ARGS__) : FN<double, 6>(__VA_ARGS__); \
+        default: break;                                                                            \
+    }
+
+// cells of one padded tile sub-grid if the scratch + column-gather spreader applies to this plan, else 0
+int nfftb_peer_tile_cells(nfftb200_plan* p)
+{
+    if (p->D != 3) return 0;
+    PEER_DISPATCH(peer_cells, p)
+    return 0;
+}
+
+int nfftb_peer_spread(nfftb200_plan* p, const void* d_fhat, void* d_scratch, int64_t t_lo, int64_t t_hi)
+{
+    PEER_DISPATCH(peer_spread, p, d_fhat, d_scratch, (int)t_lo, (int)t_hi)
+    return nfftb_fail(p, NFFTB200_UNSUPPORTED, "peer spread: unsupported m");
+}
+
+int nfftb_peer_gather(nfftb200_plan* p, void* d_slab, int layer_lo, int nlayers, const PeerTab& pt)
+{
+    PEER_DISPATCH(peer_gather, p, d_slab, layer_lo, nlayers, pt)
+    return nfftb_fail(p, NFFTB200_UNSUPPORTED, "peer gather: unsupported m");
 }
 
 int nfftb_spread(nfftb200_plan* p, const void* d_fhat, void* d_g, int B, int is_complex, int64_t t_lo,

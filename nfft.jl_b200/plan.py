@@ -531,6 +531,11 @@ class B200NFFTPlan:
         _check(self._h, self._L.nfftb200_fft(self._h, int(direction)))
 
     # ---- multi-GPU -----------------------------------------------------------------------------------
+    @property
+    def fused_peer_spread(self) -> bool:
+        """True if the node-sharded adjoint uses the fused spread + slab gather over peer memory"""
+        return bool(self._L.nfftb200_comm_is_fused(self._h))
+
     def comm_init(self, unique_id: bytes, rank: int, nranks: int, mode: int):
         buf = C.create_string_buffer(unique_id, 128)
         _check(self._h, self._L.nfftb200_comm_init(self._h, buf, rank, nranks, mode))

@@ -10,6 +10,7 @@ from oracle import nfft_oracle as O
 CFG = {"C4s": ((2 ** 21,), 2 ** 24, 4, np.float64), "C5s": ((256, 256, 256), 2 ** 25, 3, np.float32),
        "C2": ((128, 128, 128), 2 ** 21, 3, np.float32)}
 name = sys.argv[1] if len(sys.argv) > 1 else "C5s"
+kmode = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 6 = NCCL reduce-scatter baseline instead of the fused peer gather
 N, M, m, T = CFG[name]
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
@@ -19,6 +20,7 @@ real_stdout = os.dup(1); os.dup2(2, 1)
 k = O.random_nodes(M, len(N), T, seed=1)
 kd = torch.from_numpy(np.ascontiguousarray(k.T)).cuda()
 p = nb.plan_nfft(kd, N, m=m, σ=2.0, shard="nodes" if world > 1 else None)
+p.set_kernel_mode(kmode)
 f = p.empty_image(); fh = p.empty_out(); fo = p.empty_image(); fho = p.empty_out()
 f.copy_(torch.randn(f.shape, device="cuda", dtype=torch.float32 if T == np.float32 else torch.float64))
 fh.copy_(torch.randn(fh.shape, device="cuda", dtype=torch.float32 if T == np.float32 else torch.float64))
@@ -38,7 +40,8 @@ t = torch.tensor([tf, ta], device="cuda", dtype=torch.float64)
 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     os.dup2(real_stdout, 1)
-    print(json.dumps({"config": name, "N": N, "M": M, "n_gpus": world, "sharding": "nodes" if world > 1 else "none",
+    print(json.dumps({"config": name, "N": N, "M": M, "n_gpus": world, "sharding": "nodes" if world > 1 else "none", "kernel_mode": kmode,
+                      "fused_peer_spread": bool(world > 1 and p.fused_peer_spread and kmode != 6),
                       "forward_ms": t[0].item(), "adjoint_ms": t[1].item(),
                       "forward_pts_per_s": M / t[0].item() * 1e3, "adjoint_pts_per_s": M / t[1].item() * 1e3}), flush=True)
 if world > 1: dist.destroy_process_group()

@@ -23,10 +23,13 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{lr}"))
     ok = True
-    for N, T, m, M in [((32, 32, 32), np.float32, 3, 20000), ((64, 48), np.float64, 4, 9000), ((4096,), np.float64, 4, 30000),
-                       ((24, 16, 40), np.float64, 4, 7000)]:
+    for N, T, m, M, half in [((32, 32, 32), np.float32, 3, 20000, False), ((64, 48), np.float64, 4, 9000, False),
+                             ((4096,), np.float64, 4, 30000, False), ((24, 16, 40), np.float64, 4, 7000, False),
+                             ((40, 24, 64), np.float64, 4, 30000, True), ((64, 64, 64), np.float32, 3, 200000, True)]:
         D = len(N)
         k = O.random_nodes(M, D, T, seed=3)
+        if half:            # all nodes in one half of the z range: the tile cuts do not line up with the slabs
+            k[:, -1] = np.abs(k[:, -1]) * T(0.9)
         p = nb.plan_nfft(k.T, N, m=m, σ=2.0, shard="nodes")
         po = O.OraclePlan(k, N, m=m, sigma=2.0, blockSize=p.params.blockSize)
         fh = O.random_complex(M, T, 5); f = O.random_complex(N, T, 6)
@@ -43,6 +46,20 @@ def main():
         others = np.setdiff1d(np.arange(M), mine)
         untouched = bool(np.all(out[others] == 0))
         good = e1 < tol and e2 < tol and untouched
+        fused = p.fused_peer_spread
+        if D == 3:
+            # the fused spread + slab gather over peer memory against the ncclReduceScatter baseline (kernel mode 6),
+            # and again after nodes! with a larger node set (scratch re-allocated and re-exported)
+            p.set_kernel_mode(6)
+            e3 = rel(p.adjoint() * fh, adj)
+            p.set_kernel_mode(0)
+            k2 = O.random_nodes(2 * M, D, T, seed=13)
+            nb.nodes_(p, k2.T)
+            fh2 = O.random_complex(2 * M, T, 15)
+            po2 = O.OraclePlan(k2, N, m=m, sigma=2.0, blockSize=p.params.blockSize)
+            e4 = rel(p.adjoint() * fh2, po2.adjoint(fh2))
+            good = good and e3 < tol and e4 < tol and p.fused_peer_spread == fused
+            print(f"[rank {rank}]   fused={fused}: vs NCCL reduce-scatter {e3:.2e}, after nodes! {e4:.2e}", flush=True)
         ok = ok and good
         print(f"[rank {rank}] nodes-sharded N={N} {T.__name__}: adjoint {e1:.2e} forward(own {mine.size} nodes) {e2:.2e} "
               f"others untouched {untouched} -> {'ok' if good else 'FAIL'}", flush=True)
