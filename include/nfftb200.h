@@ -167,8 +167,9 @@ int nfftb200_comm_unique_id(void* out128);
  * nodes; tile_start has ntiles+1 prefix sums, out receives nranks+1 tile boundaries */
 int nfftb200_partition_tiles(const int64_t* tile_start, int64_t ntiles, int nranks, int64_t* out);
 int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, int nranks, int mode);
-/* 1 if the node-sharded adjoint of this plan runs the fused spread + slab gather over peer memory (3-D tiled
- * plans whose slabs are whole tile layers, <= 8 ranks, CUDA IPC available), 0 if it uses ncclReduceScatter */
+/* bit 0: the node-sharded adjoint of this plan runs the fused spread + slab gather over peer memory (3-D tiled
+ * plans whose slabs are whole tile layers, <= 8 ranks, CUDA IPC available) instead of ncclReduceScatter;
+ * bit 1: the forward interpolates straight from the ranks' z-slabs over peer memory instead of ncclAllGather */
 int nfftb200_comm_is_fused(nfftb200_plan* p);
 
 /* ---- Toeplitz (Gram) operator, the iterative-reconstruction caller either side of the path --------------

@@ -87,6 +87,10 @@ struct CommState {
     void* peer_ptr[NFFTB_MAX_PEERS] = {};                 // mappings of the other ranks' scratch
     PeerTab tab{};
     void* d_xchg = nullptr;                               // handle exchange / barrier word
+    // forward: interpolation straight from the ranks' z-slabs instead of an all-gather of the grid
+    bool fused_fwd = false;
+    void* slab_ptr[NFFTB_MAX_PEERS] = {};                 // mappings of the other ranks' d_a
+    SlabTab slabs{};
 };
 
 struct PeerMsg {
@@ -210,8 +214,10 @@ void nfftb_comm_destroy(nfftb200_plan* p)
     if (c->have_last) cufftDestroy(c->fft_last);
     if (c->d_a) cudaFree(c->d_a);
     if (c->d_b) cudaFree(c->d_b);
-    for (int r = 0; r < NFFTB_MAX_PEERS; r++)
+    for (int r = 0; r < NFFTB_MAX_PEERS; r++) {
         if (c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
+        if (c->slab_ptr[r]) cudaIpcCloseMemHandle(c->slab_ptr[r]);
+    }
     if (c->d_peerbuf) cudaFree(c->d_peerbuf);
     if (c->d_xchg) cudaFree(c->d_xchg);
     if (c->comm && api().ok) api().CommDestroy(c->comm);
@@ -226,6 +232,57 @@ static void own_tiles(nfftb200_plan* p, int64_t& t_lo, int64_t& t_hi)
     t_lo = cut[(size_t)p->rank]; t_hi = cut[(size_t)p->rank + 1];
 }
 
+// all-gather of one PeerMsg per rank through the communicator (host-synchronous; plan-time only)
+static int exchange_msgs(nfftb200_plan* p, const PeerMsg& mine, std::vector<PeerMsg>& msg)
+{
+    CommState* c = cs(p);
+    const int P = p->nranks;
+    msg.resize((size_t)P);
+    if (!c->d_xchg) CUDA_TRY(p, cudaMalloc(&c->d_xchg, sizeof(PeerMsg) * NFFTB_MAX_PEERS));
+    CUDA_TRY(p, cudaMemcpyAsync((char*)c->d_xchg + sizeof(PeerMsg) * p->rank, &mine, sizeof(PeerMsg), cudaMemcpyHostToDevice, p->stream));
+    NCCL_TRY(p, api().AllGather((char*)c->d_xchg + sizeof(PeerMsg) * p->rank, c->d_xchg, sizeof(PeerMsg), ncclChar, c->comm, p->stream));
+    CUDA_TRY(p, cudaMemcpyAsync(msg.data(), c->d_xchg, sizeof(PeerMsg) * P, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    return NFFTB200_OK;
+}
+
+static bool all_ok(const std::vector<PeerMsg>& msg)
+{
+    for (const PeerMsg& m : msg) if (!m.ok) return false;
+    return true;
+}
+
+// Collective (comm_init): export the z-slab work buffer and map everyone else's, so that the forward transform can
+// interpolate straight from the slabs.
+static int export_slabs(nfftb200_plan* p)
+{
+    CommState* c = cs(p);
+    const int P = p->nranks;
+    c->fused_fwd = false;
+    if (P > NFFTB_MAX_PEERS || !c->slab || p->D != 3) return NFFTB200_OK;        // same decision on every rank
+    std::vector<PeerMsg> msg;
+    PeerMsg mine{};
+    mine.ok = cudaIpcGetMemHandle(&mine.h, c->d_a) == cudaSuccess ? 1 : 0;
+    if (!mine.ok) cudaGetLastError();
+    ST_TRY(exchange_msgs(p, mine, msg));
+    if (!all_ok(msg)) return NFFTB200_OK;
+    const std::vector<PeerMsg> handles = msg;
+    mine.ok = 1;
+    for (int r = 0; r < P && mine.ok; r++) {
+        if (r == p->rank) continue;
+        if (cudaIpcOpenMemHandle(&c->slab_ptr[r], handles[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError(); c->slab_ptr[r] = nullptr; mine.ok = 0;
+        }
+    }
+    ST_TRY(exchange_msgs(p, mine, msg));
+    if (!all_ok(msg)) return NFFTB200_OK;
+    c->slabs.n = P;
+    c->slabs.planes = (int)c->Os;
+    for (int r = 0; r < P; r++) c->slabs.base[r] = r == p->rank ? c->d_a : c->slab_ptr[r];
+    c->fused_fwd = true;
+    return NFFTB200_OK;
+}
+
 // Collective (every rank calls it from nodes!): size the own tile scratch for the new node set, export it and map
 // the scratch of all other ranks.  Any rank that cannot take part switches the whole group to the NCCL path.
 int nfftb_comm_after_nodes(nfftb200_plan* p)
@@ -238,15 +295,8 @@ int nfftb_comm_after_nodes(nfftb200_plan* p)
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     for (int r = 0; r < NFFTB_MAX_PEERS; r++)
         if (c->peer_ptr[r]) { cudaIpcCloseMemHandle(c->peer_ptr[r]); c->peer_ptr[r] = nullptr; }
-    if (!c->d_xchg) CUDA_TRY(p, cudaMalloc(&c->d_xchg, sizeof(PeerMsg) * NFFTB_MAX_PEERS));
-    std::vector<PeerMsg> msg((size_t)P);
-    auto exchange = [&](const PeerMsg& mine) -> int {                     // all-gather of one PeerMsg per rank
-        CUDA_TRY(p, cudaMemcpyAsync((char*)c->d_xchg + sizeof(PeerMsg) * p->rank, &mine, sizeof(PeerMsg), cudaMemcpyHostToDevice, p->stream));
-        NCCL_TRY(p, api().AllGather((char*)c->d_xchg + sizeof(PeerMsg) * p->rank, c->d_xchg, sizeof(PeerMsg), ncclChar, c->comm, p->stream));
-        CUDA_TRY(p, cudaMemcpyAsync(msg.data(), c->d_xchg, sizeof(PeerMsg) * P, cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
-        return NFFTB200_OK;
-    };
+    std::vector<PeerMsg> msg;
+    auto exchange = [&](const PeerMsg& mine) -> int { return exchange_msgs(p, mine, msg); };
     PeerMsg mine{};
     // round 1: everyone has closed its mappings (so buffers may be re-allocated) and says whether the path applies
     const int PN = nfftb_peer_tile_cells(p);
@@ -367,6 +417,21 @@ int nfftb_comm_exec_forward(nfftb200_plan* p, const void* d_f, void* d_fhat)
         else k_pack_blocks<double2><<<blocks, 256, 0, p->stream>>>((const double2*)c->d_b, (double2*)c->d_a, c->inner, c->Ms, c->Os, P, true);
         p->launches++;
         ST_TRY(exec_fft(p, c->fft_local, c->d_a, -1));
+        if (c->fused_fwd && p->kernel_mode != 6 && p->kernel_mode != 1) {
+            // no "broadcast of the grid": after a barrier (every slab is final) the own tiles are staged plane by
+            // plane from the slab that holds them; the trailing barrier keeps the slabs alive until every rank is done
+            NCCL_TRY(p, api().AllReduce(c->d_xchg, c->d_xchg, 1, ncclFloat, ncclSum, c->comm, p->stream));
+            if (p->timing) cudaEventRecord(p->ev[2], p->stream);
+            CUDA_TRY(p, cudaMemsetAsync(d_fhat, 0, (size_t)p->M * 2 * p->esz(), p->stream));
+            const int r = nfftb_peer_interp(p, c->slabs, d_fhat, t_lo, t_hi);
+            if (r >= 0) {
+                ST_TRY(r);
+                NCCL_TRY(p, api().AllReduce(c->d_xchg, c->d_xchg, 1, ncclFloat, ncclSum, c->comm, p->stream));
+                p->launches += 3;
+                if (p->timing) { cudaEventRecord(p->ev[3], p->stream); p->pending = 1; }
+                return NFFTB200_OK;
+            }
+        }
         // "broadcast the grid": all-gather of the z-slabs
         NCCL_TRY(p, api().AllGather(c->d_a, p->d_grid, slab_reals, nccl_real(p), c->comm, p->stream));
         p->launches++;
@@ -398,7 +463,8 @@ int nfftb200_comm_unique_id(void* out128)
 int nfftb200_comm_is_fused(nfftb200_plan* p)
 {
     CommState* c = p ? cs(p) : nullptr;
-    return (c && c->fused && p->shard_mode == NFFTB200_SHARD_NODES) ? 1 : 0;
+    if (!c || p->shard_mode != NFFTB200_SHARD_NODES) return 0;
+    return (c->fused ? 1 : 0) | (c->fused_fwd ? 2 : 0);
 }
 
 int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, int nranks, int mode)
@@ -427,6 +493,7 @@ int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, i
     p->rank = rank; p->nranks = nranks;
     NCCL_TRY(p, api().CommInitRank(&c->comm, nranks, id, rank));
     int st = setup_slab(p);
+    if (st == NFFTB200_OK) st = export_slabs(p);
     if (st == NFFTB200_OK) {
         p->shard_mode = NFFTB200_SHARD_NODES;
         if (p->have_nodes) st = nfftb_comm_after_nodes(p);

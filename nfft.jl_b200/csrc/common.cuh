@@ -59,6 +59,13 @@ struct PeerTab {
     int n;                               // ranks
 };
 
+// z-slabs of the oversampled grid as seen from this process: plane z lives on rank z / planes at local plane z % planes
+struct SlabTab {
+    const void* base[NFFTB_MAX_PEERS];
+    int planes;                          // planes per slab (Nt[2] / ranks)
+    int n;                               // ranks (0 = not used)
+};
+
 // ---------------------------------------------------------------------------------------
 // the plan (host side)
 // ---------------------------------------------------------------------------------------
@@ -227,6 +234,7 @@ size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs);                
 int nfftb_peer_tile_cells(nfftb200_plan* p);                                     // spread.cu (node sharding over peer memory)
 int nfftb_peer_spread(nfftb200_plan* p, const void* d_fhat, void* d_scratch, int64_t t_lo, int64_t t_hi);
 int nfftb_peer_gather(nfftb200_plan* p, void* d_slab, int layer_lo, int nlayers, const PeerTab& pt);
+int nfftb_peer_interp(nfftb200_plan* p, const SlabTab& st, void* d_fhat, int64_t t_lo, int64_t t_hi);       // interp.cu
 int nfftb_comm_after_nodes(nfftb200_plan* p);                                    // comm.cu
 int nfftb_spread_2d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi);                    // twod.cu
 int nfftb_interp_2d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi);

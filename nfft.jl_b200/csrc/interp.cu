@@ -101,12 +101,16 @@ template <typename T, int MT> struct InterpLayout {
     }
 };
 
-template <typename T, int MT>
+// PEER = true is the multi-GPU form (node sharding, comm.cu): the grid is never assembled; every z plane of a tile
+// is staged with cp.async straight from the slab of the rank that holds it (own memory or a CUDA-IPC mapping read
+// over NVLink), which replaces the all-gather of the grid by the halo planes the own tiles actually touch.
+template <typename T, int MT, bool PEER>
 __global__ void __launch_bounds__(TI_THREADS)
 k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::type* __restrict__ fhat,
                const T* __restrict__ xs, const int32_t* __restrict__ perm,
                const int32_t* __restrict__ tile_start, int tile_lo, long long M, GeomDev geo,
-               WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp, const __grid_constant__ CUtensorMap tmap, int use_tma)
+               WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp, const __grid_constant__ CUtensorMap tmap, int use_tma,
+               const __grid_constant__ SlabTab slabs)
 {
     using C = typename Cplx<T>::type;
     using RG = RowGeom<T, MT>;
@@ -129,14 +133,14 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
     const int x0 = tx * geo.bs[0] - MT, y0 = ty * geo.bs[1] - MT, z0 = tz * geo.bs[2] - MT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    g += (long long)blockIdx.y * geo.gsz;
+    if (!PEER) g += (long long)blockIdx.y * geo.gsz;
     fhat += (long long)blockIdx.y * M;
 
     // toBlock!: interior tiles (no periodic wrap) are staged by ONE TMA tensor-map load of the (PX,PY,PZ) box
     // (cp.async.bulk.tensor + mbarrier); tiles that wrap are staged row by row with cp.async.
     // (measured on B200: a box whose innermost start coordinate is not 16-byte aligned raises "illegal
     //  instruction", so Float32 tiles qualify only when their origin x0 = tx*bs - m is even, i.e. m even)
-    const bool interior = use_tma && x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + PX <= geo.Nt[0] && y0 + PY <= geo.Nt[1] &&
+    const bool interior = !PEER && use_tma && x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + PX <= geo.Nt[0] && y0 + PY <= geo.Nt[1] &&
                           z0 + PZ <= geo.Nt[2] && ((x0 * (int)sizeof(C)) & 15) == 0;
     if (interior) {
         if (threadIdx.x == 0) {
@@ -149,12 +153,19 @@ k_interp_row3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
         const int xg0 = wrapc(x0 + lane, geo.Nt[0], fw), xg1 = wrapc(x0 + lane + 32, geo.Nt[0], fw);
         const bool on0 = lane < PX, on1 = lane + 32 < PX;
         for (int z = 0; z < PZ; z++) {
-            const unsigned gz = (unsigned)wrapc(z0 + z, geo.Nt[2], fw) * geo.Nt[1];
+            unsigned gz = (unsigned)wrapc(z0 + z, geo.Nt[2], fw);
+            const C* gb = g;
+            if (PEER) {
+                const unsigned owner = gz / (unsigned)slabs.planes;
+                gb = (const C*)slabs.base[owner];
+                gz -= owner * (unsigned)slabs.planes;
+            }
+            gz *= geo.Nt[1];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int y = warp + TI_WARPS * k;
                 if (y < PY) {
-                    const C* src = g + (gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
+                    const C* src = gb + (gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
                     C* dst = tile + (z * PY + y) * PX + lane;
                     if (on0) cp_async_cell(dst, src + xg0);
                     if (on1) cp_async_cell(dst + 32, src + xg1);
@@ -343,6 +354,30 @@ template <typename T> bool make_grid_tensor_map(CUtensorMap* tm, const void* g, 
 }
 
 template <typename T, int MT>
+int peer_interp(nfftb200_plan* p, const SlabTab& st, void* fhat, int t_lo, int t_hi)
+{
+    using C = typename Cplx<T>::type;
+    GeomDev geo = make_geom<T>(p);
+    InterpLayout<T, MT> lay(geo.bs);
+    const size_t smem = lay.bytes();
+    if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
+    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
+    if (item_hi == item_lo) return NFFTB200_OK;
+    auto kern = k_interp_row3d<T, MT, true>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    if (p->timing) cudaEventRecord(p->evk[3], p->stream);
+    kern<<<dim3(item_hi - item_lo, 1), TI_THREADS, smem, p->stream>>>(nullptr, (C*)fhat, (const T*)p->d_xs, p->d_perm,
+                                                                     p->d_items, item_lo, p->M, geo, make_win<T>(p),
+                                                                     make_poly_param<T, MT>(p), tmap, 0, st);
+    if (p->timing) { cudaEventRecord(p->evk[4], p->stream); p->pending_k |= 2; }
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
+template <typename T, int MT>
 int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi)
 {
     using C = typename Cplx<T>::type;
@@ -350,7 +385,7 @@ int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, 
     InterpLayout<T, MT> lay(geo.bs);
     const size_t smem = lay.bytes();
     if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
-    auto kern = k_interp_row3d<T, MT>;
+    auto kern = k_interp_row3d<T, MT, false>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
@@ -360,7 +395,7 @@ int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, 
     const int use_tma = (p->kernel_mode != 3 && make_grid_tensor_map<T>(&tmap, g, geo, B, lay.PX, lay.PY, lay.PZ)) ? 1 : 0;
     kern<<<grid, TI_THREADS, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm,
                                                p->d_items, item_lo, p->M, geo, make_win<T>(p),
-                                               make_poly_param<T, MT>(p), tmap, use_tma);
+                                               make_poly_param<T, MT>(p), tmap, use_tma, SlabTab{});
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;
@@ -410,6 +445,20 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
 }
 
 }  // namespace
+
+// interpolate the own tile range reading the grid from the ranks' z-slabs; -1 if the tiled kernel does not apply
+int nfftb_peer_interp(nfftb200_plan* p, const SlabTab& st, void* d_fhat, int64_t t_lo, int64_t t_hi)
+{
+    if (p->D != 3) return -1;
+#define PI_CASE(MM) case MM: return p->dtype == NFFTB200_F32 ? peer_interp<float, MM>(p, st, d_fhat, (int)t_lo, (int)t_hi) \
+                                                               : peer_interp<double, MM>(p, st, d_fhat, (int)t_lo, (int)t_hi);
+    switch (p->m) {
+        PI_CASE(2) PI_CASE(3) PI_CASE(4) PI_CASE(5) PI_CASE(6)
+        default: break;
+    }
+#undef PI_CASE
+    return -1;
+}
 
 int nfftb_interp(nfftb200_plan* p, const void* d_g, void* d_fhat, int B, int is_complex, int64_t t_lo,
                  int64_t t_hi)

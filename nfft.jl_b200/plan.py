@@ -534,7 +534,12 @@ class B200NFFTPlan:
     @property
     def fused_peer_spread(self) -> bool:
         """True if the node-sharded adjoint uses the fused spread + slab gather over peer memory"""
-        return bool(self._L.nfftb200_comm_is_fused(self._h))
+        return bool(self._L.nfftb200_comm_is_fused(self._h) & 1)
+
+    @property
+    def fused_peer_interp(self) -> bool:
+        """True if the node-sharded forward interpolates from the ranks' slabs over peer memory (no all-gather)"""
+        return bool(self._L.nfftb200_comm_is_fused(self._h) & 2)
 
     def comm_init(self, unique_id: bytes, rank: int, nranks: int, mode: int):
         buf = C.create_string_buffer(unique_id, 128)

@@ -42,6 +42,7 @@ if rank == 0:
     os.dup2(real_stdout, 1)
     print(json.dumps({"config": name, "N": N, "M": M, "n_gpus": world, "sharding": "nodes" if world > 1 else "none", "kernel_mode": kmode,
                       "fused_peer_spread": bool(world > 1 and p.fused_peer_spread and kmode != 6),
+                      "fused_peer_interp": bool(world > 1 and p.fused_peer_interp and kmode != 6),
                       "forward_ms": t[0].item(), "adjoint_ms": t[1].item(),
                       "forward_pts_per_s": M / t[0].item() * 1e3, "adjoint_pts_per_s": M / t[1].item() * 1e3}), flush=True)
 if world > 1: dist.destroy_process_group()

@@ -52,6 +52,10 @@ def main():
             # and again after nodes! with a larger node set (scratch re-allocated and re-exported)
             p.set_kernel_mode(6)
             e3 = rel(p.adjoint() * fh, adj)
+            out6 = np.zeros(M, dtype=p.cT)
+            nb.mul_(out6, p, f)
+            e3 = max(e3, rel(out6[mine], out[mine]) if mine.size else 0.0)
+            good = good and bool(np.all(out6[others] == 0))
             p.set_kernel_mode(0)
             k2 = O.random_nodes(2 * M, D, T, seed=13)
             nb.nodes_(p, k2.T)
@@ -59,7 +63,8 @@ def main():
             po2 = O.OraclePlan(k2, N, m=m, sigma=2.0, blockSize=p.params.blockSize)
             e4 = rel(p.adjoint() * fh2, po2.adjoint(fh2))
             good = good and e3 < tol and e4 < tol and p.fused_peer_spread == fused
-            print(f"[rank {rank}]   fused={fused}: vs NCCL reduce-scatter {e3:.2e}, after nodes! {e4:.2e}", flush=True)
+            print(f"[rank {rank}]   fused spread={fused} interp={p.fused_peer_interp}: vs NCCL reduce-scatter/all-gather "
+                  f"{e3:.2e}, after nodes! {e4:.2e}", flush=True)
         ok = ok and good
         print(f"[rank {rank}] nodes-sharded N={N} {T.__name__}: adjoint {e1:.2e} forward(own {mine.size} nodes) {e2:.2e} "
               f"others untouched {untouched} -> {'ok' if good else 'FAIL'}", flush=True)
