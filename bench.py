@@ -205,7 +205,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ts = nb.TimingStats()
     phases = {n: 0.0 for n in ("deconv", "fft", "conv", "conv_adjoint", "fft_adjoint", "deconv_adjoint")}
-    kt = {"spread": 0.0, "interp": 0.0, "memset": 0.0}
+    kt = {"spread": 0.0, "interp": 0.0, "memset": 0.0, "gather": 0.0}
     l0 = p.launch_count()
     barrier()
     for s, e in ev:
@@ -268,7 +268,7 @@ def main():
             traffic = json.load(fh_).get("spread_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "adjoint gridding: k_spread_sub3d<float,3> + k_gather_tiles3d (convolve_transpose!)",
+    roofline = {"bound": "hbm", "kernel": "adjoint gridding: k_spread_sub3d<float,3> + k_gather_cols3d (convolve_transpose!)",
                 "achieved": abytes / t_spread / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": abytes / t_spread / 1e9 / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": abytes, "us_per_launch": t_spread * 1e6,

@@ -130,8 +130,9 @@ int nfftb200_fft(nfftb200_plan* p, int direction);
 int nfftb200_set_timing(nfftb200_plan* p, int enable);
 int nfftb200_get_timing(nfftb200_plan* p, double out[7]);
 
-/* device time of the last spread kernel, the last interpolation kernel and the last grid memset
- * (seconds, CUDA events on the plan's stream; needs set_timing(1)): out = {spread, interp, memset, 0} */
+/* device time of the last spread stage (spread kernel + gather pass), the last interpolation kernel, the last grid
+ * memset and the gather pass alone (seconds, CUDA events on the plan's stream; needs set_timing(1)):
+ * out = {spread, interp, memset, gather} */
 int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
 
 /* kernel-selection knob for benchmarking/tests:

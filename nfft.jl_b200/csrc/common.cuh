@@ -146,9 +146,10 @@ struct nfftb200_plan {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double t[7] = {0, 0, 0, 0, 0, 0, 0};
     int pending = 0;                 // 0 none, 1 forward, 2 adjoint
-    cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // memset | spread kernel | interp kernel
+    cudaEvent_t evk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // memset | spread stage | interp kernel | [5] gather start
+    bool have_gather_ev = false;
     int pending_k = 0;               // bit 0: spread events valid, bit 1: interp events valid
-    double tk[4] = {0, 0, 0, 0};     // spread kernel, interp kernel, grid memset, reserved
+    double tk[4] = {0, 0, 0, 0};     // spread stage (kernel + gather), interp kernel, grid memset, gather pass
 
     int64_t launches = 0;
     std::string err;

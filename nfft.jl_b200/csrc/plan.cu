@@ -310,7 +310,7 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
         CUDA_TRY(p, cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
         p->own_stream = true;
         for (int i = 0; i < 4; i++) CUDA_TRY(p, cudaEventCreate(&p->ev[i]));
-        for (int i = 0; i < 5; i++) CUDA_TRY(p, cudaEventCreate(&p->evk[i]));
+        for (int i = 0; i < 6; i++) CUDA_TRY(p, cudaEventCreate(&p->evk[i]));
         ST_TRY(upload_table(p, p->h_hat_inv, &p->d_hat_inv));
         ST_TRY(upload_table(p, p->h_poly, &p->d_poly));
         ST_TRY(upload_table(p, p->h_lin, &p->d_lin));
@@ -343,7 +343,7 @@ int nfftb200_destroy(nfftb200_plan* p)
                     p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab, p->d_tilebuf, p->d_items, p->d_tile_items};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 4; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
-    for (int i = 0; i < 5; i++) if (p->evk[i]) cudaEventDestroy(p->evk[i]);
+    for (int i = 0; i < 6; i++) if (p->evk[i]) cudaEventDestroy(p->evk[i]);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return NFFTB200_OK;
@@ -621,6 +621,8 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4])
         cudaEventElapsedTime(&a, p->evk[0], p->evk[1]);
         cudaEventElapsedTime(&b, p->evk[1], p->evk[2]);
         p->tk[2] = a * 1e-3; p->tk[0] = b * 1e-3;
+        p->tk[3] = 0;
+        if (p->have_gather_ev) { float c = 0; cudaEventElapsedTime(&c, p->evk[5], p->evk[2]); p->tk[3] = c * 1e-3; }
     }
     if (p->timing && (p->pending_k & 2)) {
         CUDA_TRY(p, cudaEventSynchronize(p->evk[4]));

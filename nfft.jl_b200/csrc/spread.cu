@@ -626,6 +626,7 @@ int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_l
         explicit KT(nfftb200_plan* q) : p(q) { if (p->timing) cudaEventRecord(p->evk[1], p->stream); }
         ~KT() { if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; } }
     };
+    p->have_gather_ev = false;
     if (use_scratch) {
         if (p->timing) cudaEventRecord(p->evk[0], st);
         KT kt(p);
@@ -633,6 +634,7 @@ int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_l
         CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SS_THREADS, smem, st>>>((const C*)fhat, (C*)g, (C*)p->d_tilebuf, (const T*)p->d_xs, p->d_perm,
                                             p->d_items, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
+        if (p->timing) { cudaEventRecord(p->evk[5], st); p->have_gather_ev = true; }
         const int units = geo.Nt[0] / 2;                                   // Nt[0] is even; one thread per cell pair
         int bx = 32;
         if (p->kernel_mode != 5 && geo.bs[2] == 16 && geo.Nt[2] % 16 == 0 && 16 >= 2 * MT) {

@@ -267,10 +267,10 @@ class B200NFFTPlan:
         _check(self._h, self._L.nfftb200_set_kernel_mode(self._h, int(mode)))
 
     def kernel_times(self):
-        """device seconds of the last (spread kernel, interp kernel, grid memset); needs timing enabled"""
+        """device seconds of the last spread stage (kernel + gather), interp kernel, grid memset and gather pass"""
         t = (C.c_double * 4)()
         _check(self._h, self._L.nfftb200_get_kernel_times(self._h, t))
-        return {"spread": t[0], "interp": t[1], "memset": t[2]}
+        return {"spread": t[0], "interp": t[1], "memset": t[2], "gather": t[3]}
 
     def enable_timing(self, on=True):
         self._L.nfftb200_set_timing(self._h, int(on))
