@@ -62,8 +62,11 @@ enum {
     NFFTB200_COSH_TYPE = 4
 };
 
-/* where caller buffers live */
-enum { NFFTB200_HOST = 0, NFFTB200_DEVICE = 1 };
+/* where caller buffers live.  NFFTB200_HOST calls return when the result is in the caller's buffer.
+ * NFFTB200_HOST_ASYNC (exec_forward / exec_adjoint only) takes page-locked host buffers and returns at once: the
+ * upload, the transform and the download are queued on three internal streams, so that back-to-back calls overlap
+ * their copies with each other's kernels; the buffers belong to the library until nfftb200_sync returns. */
+enum { NFFTB200_HOST = 0, NFFTB200_DEVICE = 1, NFFTB200_HOST_ASYNC = 2 };
 
 /* sharding mode for multi-GPU plans (new; no reference counterpart) */
 enum { NFFTB200_SHARD_NONE = 0, NFFTB200_SHARD_BATCH = 1, NFFTB200_SHARD_NODES = 2 };

@@ -141,6 +141,14 @@ struct nfftb200_plan {
     void* d_stage_k = nullptr;  int64_t cap_stage_k = 0;     // bytes
     void* d_stage_g = nullptr;  int64_t cap_stage_g = 0;     // bytes
 
+    // asynchronous host-buffer mode (where = NFFTB200_HOST_ASYNC): uploads, compute and downloads run on three
+    // streams chained by events, each direction with its own input and output staging buffer, so that the copies of
+    // one call overlap the kernels of the neighbouring calls; nfftb200_sync waits for everything
+    struct AsyncSlot { void* d = nullptr; int64_t cap = 0; cudaEvent_t free_ev = nullptr; bool used = false; };
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    cudaEvent_t e_up = nullptr, e_done = nullptr;
+    AsyncSlot a_in[2], a_out[2];      // [0] forward, [1] adjoint
+
     // timing
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

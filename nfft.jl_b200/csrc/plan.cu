@@ -194,6 +194,61 @@ int stage_back(nfftb200_plan* p, void* dst, const void* dsrc, int64_t bytes, int
     return NFFTB200_OK;
 }
 
+// ---- asynchronous host-buffer mode -----------------------------------------------------------------------
+int async_setup(nfftb200_plan* p, int dir, int64_t bytes_in, int64_t bytes_out)
+{
+    if (!p->s_up) {
+        CUDA_TRY(p, cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking));
+        CUDA_TRY(p, cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking));
+        CUDA_TRY(p, cudaEventCreateWithFlags(&p->e_up, cudaEventDisableTiming));
+        CUDA_TRY(p, cudaEventCreateWithFlags(&p->e_done, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(p, cudaEventCreateWithFlags(&p->a_in[i].free_ev, cudaEventDisableTiming));
+            CUDA_TRY(p, cudaEventCreateWithFlags(&p->a_out[i].free_ev, cudaEventDisableTiming));
+        }
+    }
+    nfftb200_plan::AsyncSlot* slots[2] = {&p->a_in[dir], &p->a_out[dir]};
+    const int64_t need[2] = {bytes_in, bytes_out};
+    for (int i = 0; i < 2; i++) {
+        if (need[i] <= slots[i]->cap) continue;
+        // growing a staging buffer: nothing may still be using the old one
+        CUDA_TRY(p, cudaStreamSynchronize(p->s_up));
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+        CUDA_TRY(p, cudaStreamSynchronize(p->s_down));
+        ST_TRY(ensure(p, &slots[i]->d, &slots[i]->cap, need[i]));
+        slots[i]->used = false;
+    }
+    return NFFTB200_OK;
+}
+
+// upload `src` into the direction's input slot on the upload stream; the compute stream waits for it and for the
+// previous download out of the output slot
+int async_begin(nfftb200_plan* p, int dir, const void* src, int64_t bytes_in)
+{
+    nfftb200_plan::AsyncSlot& in = p->a_in[dir];
+    nfftb200_plan::AsyncSlot& out = p->a_out[dir];
+    if (in.used) CUDA_TRY(p, cudaStreamWaitEvent(p->s_up, in.free_ev, 0));
+    CUDA_TRY(p, cudaMemcpyAsync(in.d, src, (size_t)bytes_in, cudaMemcpyHostToDevice, p->s_up));
+    CUDA_TRY(p, cudaEventRecord(p->e_up, p->s_up));
+    CUDA_TRY(p, cudaStreamWaitEvent(p->stream, p->e_up, 0));
+    if (out.used) CUDA_TRY(p, cudaStreamWaitEvent(p->stream, out.free_ev, 0));
+    return NFFTB200_OK;
+}
+
+// the transform is queued: release the input slot, download the output slot on the download stream
+int async_end(nfftb200_plan* p, int dir, void* dst, int64_t bytes_out)
+{
+    nfftb200_plan::AsyncSlot& in = p->a_in[dir];
+    nfftb200_plan::AsyncSlot& out = p->a_out[dir];
+    CUDA_TRY(p, cudaEventRecord(in.free_ev, p->stream));
+    CUDA_TRY(p, cudaEventRecord(p->e_done, p->stream));
+    CUDA_TRY(p, cudaStreamWaitEvent(p->s_down, p->e_done, 0));
+    CUDA_TRY(p, cudaMemcpyAsync(dst, out.d, (size_t)bytes_out, cudaMemcpyDeviceToHost, p->s_down));
+    CUDA_TRY(p, cudaEventRecord(out.free_ev, p->s_down));
+    in.used = out.used = true;
+    return NFFTB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -334,7 +389,19 @@ int nfftb200_destroy(nfftb200_plan* p)
 {
     if (!p) return NFFTB200_OK;
     DeviceGuard guard(p->device);
+    if (p->s_up) cudaStreamSynchronize(p->s_up);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->s_down) cudaStreamSynchronize(p->s_down);
+    for (int i = 0; i < 2; i++) {
+        if (p->a_in[i].d) cudaFree(p->a_in[i].d);
+        if (p->a_out[i].d) cudaFree(p->a_out[i].d);
+        if (p->a_in[i].free_ev) cudaEventDestroy(p->a_in[i].free_ev);
+        if (p->a_out[i].free_ev) cudaEventDestroy(p->a_out[i].free_ev);
+    }
+    if (p->e_up) cudaEventDestroy(p->e_up);
+    if (p->e_done) cudaEventDestroy(p->e_done);
+    if (p->s_up) cudaStreamDestroy(p->s_up);
+    if (p->s_down) cudaStreamDestroy(p->s_down);
     nfftb_comm_destroy(p);
     if (p->have_fft) cufftDestroy(p->fft);
     if (p->have_pruned) { cufftDestroy(p->fft_xy); cufftDestroy(p->fft_z); }
@@ -470,8 +537,15 @@ int nfftb200_exec_forward(nfftb200_plan* p, const void* f, void* fHat, int where
     const int64_t csz = 2 * (int64_t)p->esz();
     const void* df = nullptr;
     void* dh = nullptr;
-    ST_TRY(stage_in(p, f, p->fsz * p->B * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
-    ST_TRY(stage_out_buf(p, fHat, p->M * p->B * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
+    const bool async = where == NFFTB200_HOST_ASYNC;
+    if (async) {
+        ST_TRY(async_setup(p, 0, p->fsz * p->B * csz, p->M * p->B * csz));
+        ST_TRY(async_begin(p, 0, f, p->fsz * p->B * csz));
+        df = p->a_in[0].d; dh = p->a_out[0].d;
+    } else {
+        ST_TRY(stage_in(p, f, p->fsz * p->B * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
+        ST_TRY(stage_out_buf(p, fHat, p->M * p->B * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
+    }
     if (p->shard_mode == NFFTB200_SHARD_NODES) {
         ST_TRY(nfftb_comm_exec_forward(p, df, dh));
     } else {
@@ -484,6 +558,7 @@ int nfftb200_exec_forward(nfftb200_plan* p, const void* f, void* fHat, int where
         rec(p, 3);
         p->pending = 1;
     }
+    if (async) return async_end(p, 0, fHat, p->M * p->B * csz);
     return stage_back(p, fHat, dh, p->M * p->B * csz, where);
 }
 
@@ -495,8 +570,15 @@ int nfftb200_exec_adjoint(nfftb200_plan* p, const void* fHat, void* f, int where
     const int64_t csz = 2 * (int64_t)p->esz();
     const void* dh = nullptr;
     void* df = nullptr;
-    ST_TRY(stage_in(p, fHat, p->M * p->B * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
-    ST_TRY(stage_out_buf(p, f, p->fsz * p->B * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
+    const bool async = where == NFFTB200_HOST_ASYNC;
+    if (async) {
+        ST_TRY(async_setup(p, 1, p->M * p->B * csz, p->fsz * p->B * csz));
+        ST_TRY(async_begin(p, 1, fHat, p->M * p->B * csz));
+        dh = p->a_in[1].d; df = p->a_out[1].d;
+    } else {
+        ST_TRY(stage_in(p, fHat, p->M * p->B * csz, where, &p->d_stage_h, &p->cap_stage_h, &dh));
+        ST_TRY(stage_out_buf(p, f, p->fsz * p->B * csz, where, &p->d_stage_f, &p->cap_stage_f, &df));
+    }
     if (p->shard_mode == NFFTB200_SHARD_NODES) {
         ST_TRY(nfftb_comm_exec_adjoint(p, dh, df));
     } else {
@@ -509,6 +591,7 @@ int nfftb200_exec_adjoint(nfftb200_plan* p, const void* fHat, void* f, int where
         rec(p, 3);
         p->pending = 2;
     }
+    if (async) return async_end(p, 1, f, p->fsz * p->B * csz);
     return stage_back(p, f, df, p->fsz * p->B * csz, where);
 }
 
@@ -667,7 +750,9 @@ int nfftb200_sync(nfftb200_plan* p)
     if (!p) return NFFTB200_BAD_ARGUMENT;
     if (p->device < 0) return NFFTB200_OK;
     DeviceGuard guard(p->device);
+    if (p->s_up) CUDA_TRY(p, cudaStreamSynchronize(p->s_up));
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    if (p->s_down) CUDA_TRY(p, cudaStreamSynchronize(p->s_down));
     return NFFTB200_OK;
 }
 

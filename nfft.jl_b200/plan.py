@@ -91,7 +91,7 @@ class NFFTParams:
 _STATUS_EXC = {1: ArgumentError, 2: ArgumentError, 3: DimensionMismatch, 4: NotImplementedError,
                5: RuntimeError, 6: RuntimeError, 7: MemoryError, 8: ArgumentError, 9: RuntimeError}
 
-HOST, DEVICE = 0, 1
+HOST, DEVICE, HOST_ASYNC = 0, 1, 2
 
 
 def _check(handle, status):
@@ -211,6 +211,7 @@ class B200NFFTPlan:
         if stream == "current" and torch is not None and torch.cuda.is_available():
             self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._timing_on = False
+        self._async_keep = []
         self.J = 0
         self.NOut = (0,)
         self.k = None
@@ -262,6 +263,7 @@ class B200NFFTPlan:
 
     def sync(self):
         _check(self._h, self._L.nfftb200_sync(self._h))
+        self._async_keep = []
 
     def set_kernel_mode(self, mode: int):
         _check(self._h, self._L.nfftb200_set_kernel_mode(self._h, int(mode)))
@@ -423,7 +425,14 @@ class B200NFFTPlan:
         timing.pre = pre or timing.pre
 
     # ---- mul!  src/implementation.jl:155-193 -------------------------------------------------------
-    def mul_forward(self, fHat, f, timing=None, verbose=False):
+    def _async_host(self, bi, bo):
+        """asynchronous host mode: page-locked numpy buffers, no conversions; they belong to the plan until sync()"""
+        if bi.where != HOST or bo.where != HOST or bo.copied_from is not None:
+            raise ArgumentError("async_host needs numpy (page-locked) buffers of the plan's dtype in Fortran order")
+        self._async_keep += [bi.keep, bo.keep]
+        return HOST_ASYNC
+
+    def mul_forward(self, fHat, f, timing=None, verbose=False, async_host=False):
         # consistencyCheck, src/utils.jl:98-105
         if tuple(f.shape) != self._bshape(self.N) or tuple(fHat.shape) != self._bshape(self.NOut):
             raise DimensionMismatch("Data is not consistent with NFFTPlan")
@@ -432,6 +441,8 @@ class B200NFFTPlan:
         bo = self._out(fHat, self._bshape(self.NOut), self.cT, "fHat")
         where = DEVICE if (bi.where == DEVICE and bo.where == DEVICE) else HOST
         bi, bo = self._same_side(bi, bo, where)
+        if async_host:
+            where = self._async_host(bi, bo)
         _check(self._h, self._L.nfftb200_exec_forward(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr), where))
         self._finish(bo)
         self._fill_timing(timing)
@@ -439,7 +450,7 @@ class B200NFFTPlan:
             print(f"Timing: deconv={timing.deconv} fft={timing.fft} conv={timing.conv}")
         return fHat
 
-    def mul_adjoint(self, f, fHat, timing=None, verbose=False):
+    def mul_adjoint(self, f, fHat, timing=None, verbose=False, async_host=False):
         if tuple(f.shape) != self._bshape(self.N) or tuple(fHat.shape) != self._bshape(self.NOut):
             raise DimensionMismatch("Data is not consistent with NFFTPlan")
         self._timing(timing)
@@ -447,6 +458,8 @@ class B200NFFTPlan:
         bo = self._out(f, self._bshape(self.N), self.cT, "f")
         where = DEVICE if (bi.where == DEVICE and bo.where == DEVICE) else HOST
         bi, bo = self._same_side(bi, bo, where)
+        if async_host:
+            where = self._async_host(bi, bo)
         _check(self._h, self._L.nfftb200_exec_adjoint(self._h, C.c_void_p(bi.ptr), C.c_void_p(bo.ptr), where))
         self._finish(bo)
         self._fill_timing(timing)
@@ -596,11 +609,12 @@ def adjoint(p):
     return p.adjoint()
 
 
-def mul_(out, p, x, timing=None, verbose=False):
-    """mul!(fHat, p, f) / mul!(f, adjoint(p), fHat)"""
+def mul_(out, p, x, timing=None, verbose=False, async_host=False):
+    """mul!(fHat, p, f) / mul!(f, adjoint(p), fHat).  async_host=True queues upload, transform and download of
+    page-locked numpy buffers and returns at once (NFFTB200_HOST_ASYNC); call p.sync() before touching them."""
     if isinstance(p, AdjointPlan):
-        return p.parent.mul_adjoint(out, x, timing=timing, verbose=verbose)
-    return p.mul_forward(out, x, timing=timing, verbose=verbose)
+        return p.parent.mul_adjoint(out, x, timing=timing, verbose=verbose, async_host=async_host)
+    return p.mul_forward(out, x, timing=timing, verbose=verbose, async_host=async_host)
 
 
 def convolve_(p, g, fHat):

@@ -558,3 +558,37 @@ def test_toeplitz_convolve(nb):
     nb.convolveToeplitzKernel_(y3, K3)
     assert rel(y3, p3.adjoint() * (p3 * x3)) < 1e-9
     assert rel(y3, O.convolve_toeplitz_kernel(x3, K3)) < 1e-12
+
+
+def test_async_host_mode_pipelines_and_matches(nb):
+    """NFFTB200_HOST_ASYNC: queued forward/adjoint calls on page-locked host buffers give bit-identical results to the
+    synchronous host calls, also when the same plan is re-used back to back with different inputs"""
+    import torch
+    N, T, M = (24, 20, 18), np.float32, 9000
+    k = O.random_nodes(M, 3, T, seed=41)
+    p = nb.plan_nfft(k.T, N, m=3, σ=2.0)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    fs = [np.asfortranarray(pin(np.ascontiguousarray(O.random_complex(N, T, 50 + i).T)).T) for i in range(3)]
+    fhs = [pin(O.random_complex(M, T, 60 + i)) for i in range(3)]
+    ref_f = [p * f for f in fs]
+    ref_a = [p.adjoint() * fh for fh in fhs]
+    out_f = [pin(np.zeros(M, dtype=np.complex64)) for _ in range(3)]
+    out_a = [np.asfortranarray(pin(np.zeros(N[::-1], dtype=np.complex64)).T) for _ in range(3)]
+    for rep in range(2):
+        for i in range(3):
+            nb.mul_(out_f[i], p, fs[i], async_host=True)
+            nb.mul_(out_a[i], p.adjoint(), fhs[i], async_host=True)
+        p.sync()
+        for i in range(3):
+            assert np.array_equal(out_f[i], ref_f[i]) and np.array_equal(out_a[i], ref_a[i])
+            out_f[i][...] = 0; out_a[i][...] = 0
+    with pytest.raises(nb.ArgumentError):                     # conversions are not possible behind an asynchronous call
+        nb.mul_(np.zeros(M, dtype=np.complex128), p, fs[0], async_host=True)
+    # nodes! with more nodes while nothing is in flight: staging buffers grow
+    k2 = O.random_nodes(2 * M, 3, T, seed=42)
+    nb.nodes_(p, k2.T)
+    fh2 = pin(O.random_complex(2 * M, T, 70))
+    o2 = np.asfortranarray(pin(np.zeros(N[::-1], dtype=np.complex64)).T)
+    nb.mul_(o2, p.adjoint(), fh2, async_host=True)
+    p.sync()
+    assert np.array_equal(o2, p.adjoint() * fh2)
