@@ -84,7 +84,9 @@ k_spread_generic(const void* __restrict__ fhat_, void* __restrict__ g_, const T*
 // ---------------------------------------------------------------------------------------
 // tiled 3-D spreader: warp-private padded sub-tiles, row-per-lane accumulation
 // ---------------------------------------------------------------------------------------
-constexpr int SS_CHUNK = 512;        // nodes staged per pass (coordinates, values, octant ids in shared memory)
+// nodes staged per pass (coordinates, values, octant ids in shared memory).  Float32: 768, so that a default 16^3
+// tile of the C2 density (512 +- 23 nodes) is always ONE pass; Float64 keeps 512 (its sub-tiles leave less room).
+template <typename T> struct SSChunk { static constexpr int value = sizeof(T) == 4 ? 768 : 512; };
 
 // NW = 8: octants 2x2x2, one CTA per SM;  NW = 4: quadrants 2x2x1 (for tiles that are half as thick), two CTAs
 // per SM so that one CTA's shared-memory-bound accumulation overlaps the other's weight/merge/flush phases.
@@ -102,8 +104,8 @@ template <typename T, int MT, int NW> struct SubLayout {
     __host__ __device__ size_t bytes() const
     {
         return sizeof(typename Cplx<T>::type) * (size_t)NW * QN + sizeof(T) * NW * 32 * RW +
-               sizeof(int) * NW * 32 + sizeof(unsigned short) * NW * 64 + SS_CHUNK +
-               sizeof(T) * 3 * SS_CHUNK + sizeof(typename Cplx<T>::type) * SS_CHUNK + 16;
+               sizeof(int) * NW * 32 + sizeof(unsigned short) * NW * 64 + SSChunk<T>::value +
+               sizeof(T) * 3 * SSChunk<T>::value + sizeof(typename Cplx<T>::type) * SSChunk<T>::value + 16;
     }
 };
 
@@ -119,7 +121,7 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     using RG = RowGeom<T, MT>;
     using SL = SubLayout<T, MT, NW>;
     constexpr int L = 2 * MT, VPC = RG::VPC, NV = RG::NV, NWX = RG::NWX, RW = SL::RW;
-    constexpr int SS_WARPS = NW, SS_THREADS = NW * 32;
+    constexpr int SS_WARPS = NW, SS_THREADS = NW * 32, SS_CHUNK = SSChunk<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SL lay(geo.bs);
     const int QX = lay.QX, QY = lay.QY, QN = lay.QN;
@@ -339,41 +341,61 @@ k_spread_sub3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     {
         const int SX = lay.SX, SY = lay.SY, SZ = lay.SZ, QZ = lay.QZ;
         const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
+        // every fold adds whole runs of cells; runs are moved as 16-byte units when the geometry keeps them aligned
+        // (always true for the default tiles: even QX, even SX)
+        constexpr int VC = 16 / (int)sizeof(C);                   // cells per 16-byte unit
+        const bool vec = (VC == 1) || ((QX % 2 == 0) && (SX % 2 == 0) && (L % 2 == 0));
+        auto fold = [&](C* d, const C* a) {                       // *d += *a for one 16-byte unit
+            if (VC == 2) {
+                float4 x = *reinterpret_cast<const float4*>(a), y = *reinterpret_cast<float4*>(d);
+                y.x += x.x; y.y += x.y; y.z += x.z; y.w += x.w;
+                *reinterpret_cast<float4*>(d) = y;
+            } else { C c = *d; c.x += a->x; c.y += a->y; *d = c; }
+        };
+        auto fold1 = [&](C* d, const C* a) { C c = *d; c.x += a->x; c.y += a->y; *d = c; };
         if (NW == 8) {   // z
             const int blk = L * QY * QX;
-            for (int q = threadIdx.x; q < 4 * blk; q += SS_THREADS) {
-                const int col = q / blk, r = q - col * blk;
-                const C a = sub[col * QN + SZ * QY * QX + r];
-                C* d = sub + (col + 4) * QN + r;
-                C c = *d; c.x += a.x; c.y += a.y; *d = c;
+            if (vec) {
+                const int nb = blk / VC;
+                for (int q = threadIdx.x; q < 4 * nb; q += SS_THREADS) {
+                    const int col = q / nb, r = (q - col * nb) * VC;
+                    fold(sub + (col + 4) * QN + r, sub + col * QN + SZ * QY * QX + r);
+                }
+            } else {
+                for (int q = threadIdx.x; q < 4 * blk; q += SS_THREADS) {
+                    const int col = q / blk, r = q - col * blk;
+                    fold1(sub + (col + 4) * QN + r, sub + col * QN + SZ * QY * QX + r);
+                }
             }
         }
         if (NW == 8) __syncthreads();
         {   // y: live planes of octant oz: oz==0 -> [0,SZ), oz==1 -> [0,QZ)   (NW == 4: a single z layer, all planes live)
             const int blk = L * QX, npl = (NW == 8) ? SZ + QZ : QZ;
-            const unsigned inv = fastdiv_inv(blk);
-            for (int q = threadIdx.x; q < 2 * npl * blk; q += SS_THREADS) {
-                const int pb = (int)fastdiv(q, inv), r = q - pb * blk;
+            const int step = vec ? VC : 1, nb = blk / step;
+            const unsigned inv = fastdiv_inv(nb);
+            for (int q = threadIdx.x; q < 2 * npl * nb; q += SS_THREADS) {
+                const int pb = (int)fastdiv(q, inv), r = (q - pb * nb) * step;
                 const int ox_ = pb >= npl, pl = pb - ox_ * npl;
                 const int oz_ = (NW == 8) ? (pl >= SZ) : 0, zz = pl - oz_ * SZ;
                 const int o = ox_ + 4 * oz_;
-                const C a = sub[o * QN + (zz * QY + SY) * QX + r];
+                const C* a = sub + o * QN + (zz * QY + SY) * QX + r;
                 C* d = sub + (o + 2) * QN + zz * QY * QX + r;
-                C c = *d; c.x += a.x; c.y += a.y; *d = c;
+                if (vec) fold(d, a); else fold1(d, a);
             }
         }
         __syncthreads();
         {   // x: live rows: merged (y,z) coordinates of the padded tile
-            const unsigned invL = fastdiv_inv(L), invPY = fastdiv_inv(PY);
-            for (int q = threadIdx.x; q < PY * PZ * L; q += SS_THREADS) {
-                const int row = (int)fastdiv(q, invL), xx = q - row * L;
+            const int step = vec ? VC : 1, nx = L / step;
+            const unsigned invL = fastdiv_inv(nx), invPY = fastdiv_inv(PY);
+            for (int q = threadIdx.x; q < PY * PZ * nx; q += SS_THREADS) {
+                const int row = (int)fastdiv(q, invL), xx = (q - row * nx) * step;
                 const int z = (int)fastdiv(row, invPY), y = row - z * PY;
                 const int oy_ = y >= SY, oz_ = (NW == 8) ? (z >= SZ) : 0;
                 const int o = 2 * oy_ + 4 * oz_;
                 const int ro = ((z - oz_ * SZ) * QY + (y - oy_ * SY)) * QX;
-                const C a = sub[o * QN + ro + SX + xx];
+                const C* a = sub + o * QN + ro + SX + xx;
                 C* d = sub + (o + 1) * QN + ro + xx;
-                C c = *d; c.x += a.x; c.y += a.y; *d = c;
+                if (vec) fold(d, a); else fold1(d, a);
             }
         }
         __syncthreads();
