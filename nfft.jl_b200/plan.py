@@ -170,6 +170,7 @@ class B200NFFTPlan:
         self.T = T
         self.cT = np.complex64 if T == np.float32 else np.complex128
         m_, σ_, reltol_ = accuracyParams(m, σ, reltol)
+        self._requested = (m_, σ_)
         self._L = _lib.lib()
         if device is None:
             device = k.device.index if (k_is_torch and k.is_cuda) else (
@@ -239,6 +240,21 @@ class B200NFFTPlan:
         if h is not None and h.value:
             self._L.nfftb200_destroy(h)
             self._h = C.c_void_p()
+
+    def copy(self):
+        """Base.copy(p::NFFTPlan) (src/implementation.jl:45-66): an independent plan with the same parameters and
+        nodes and its own grid, FFT plans, scratch and stream state -- what a second task needs, since a plan is not
+        re-entrant.  (Sharded plans are collective objects and cannot be copied.)"""
+        if self.shard is not None:
+            raise ArgumentError("a sharded plan cannot be copied")
+        q = B200NFFTPlan(self.k, self.N, m=self._requested[0], σ=self._requested[1], window=self.params.window,
+                         precompute=self.params.precompute, blockSize=self.params.blockSize,
+                         ntransforms=self.ntransforms, device=self.device, sortNodes=False,
+                         storeDeconvolutionIdx=self.params.storeDeconvolutionIdx, blocking=self.params.blocking)
+        q.params = dataclasses.replace(self.params)
+        return q
+
+    __copy__ = copy
 
     def __repr__(self):
         return (f"B200NFFTPlan with {self.J} sampling points for an input array of size{self.N} and an "
@@ -581,6 +597,11 @@ class AdjointPlan:
         return p.mul_adjoint(out, fHat)
 
     __matmul__ = __mul__
+
+    def copy(self):
+        return AdjointPlan(self.parent.copy())
+
+    __copy__ = copy
 
     def __repr__(self):
         return "Adjoint of " + repr(self.parent)

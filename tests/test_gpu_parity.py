@@ -592,3 +592,21 @@ def test_async_host_mode_pipelines_and_matches(nb):
     nb.mul_(o2, p.adjoint(), fh2, async_host=True)
     p.sync()
     assert np.array_equal(o2, p.adjoint() * fh2)
+
+
+def test_copy_gives_independent_plan(nb):
+    """test/constructors.jl:17-28: copy(p) has the same parameters and results, its own grid/scratch; copy(adjoint(p))
+    does not error"""
+    import copy as _copy
+    k = O.random_nodes(500, 2, np.float64, seed=81)
+    p = nb.plan_nfft(k.T, (12, 14), m=4, σ=2.0, window="cosh_type", precompute=nb.LINEAR)
+    q = _copy.copy(p)
+    assert q.params == p.params and q.N == p.N and q.Ñ == p.Ñ and q.J == p.J
+    assert q.tmpVec.data_ptr() != p.tmpVec.data_ptr()
+    f = O.random_complex((12, 14), np.float64, 82)
+    assert np.array_equal(p * f, q * f)
+    p.destroy()
+    fh = O.random_complex(500, np.float64, 83)
+    qa = q.adjoint().copy()
+    assert np.array_equal(qa * fh, q.adjoint() * fh)
+    assert "Adjoint of B200NFFTPlan with 500 sampling points" in repr(qa)
