@@ -149,6 +149,12 @@ struct nfftb200_plan {
     cudaEvent_t e_up = nullptr, e_done = nullptr;
     AsyncSlot a_in[2], a_out[2];      // [0] forward, [1] adjoint
 
+    // Toeplitz kernel construction (toeplitz.cu): image-sized cuFFT plan and work arrays, kept across calls
+    cufftHandle fft_img = 0;
+    bool have_fft_img = false;
+    void* d_toep[3] = {nullptr, nullptr, nullptr};     // ones (M), image (fsz), shifted image (fsz)
+    int64_t cap_toep[3] = {0, 0, 0};
+
     // timing
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

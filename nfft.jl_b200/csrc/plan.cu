@@ -398,6 +398,8 @@ int nfftb200_destroy(nfftb200_plan* p)
         if (p->a_in[i].free_ev) cudaEventDestroy(p->a_in[i].free_ev);
         if (p->a_out[i].free_ev) cudaEventDestroy(p->a_out[i].free_ev);
     }
+    if (p->have_fft_img) cufftDestroy(p->fft_img);
+    for (void* b : p->d_toep) if (b) cudaFree(b);
     if (p->e_up) cudaEventDestroy(p->e_up);
     if (p->e_done) cudaEventDestroy(p->e_done);
     if (p->s_up) cudaStreamDestroy(p->s_up);

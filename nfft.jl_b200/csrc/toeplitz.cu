@@ -133,47 +133,47 @@ int nfftb200_toeplitz_kernel(nfftb200_plan* p, void* lambda, int where)
     if (p->B != 1) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "Toeplitz kernel needs a plan with ntransforms = 1");
     Dev guard(p->device);
     const size_t csz = 2 * p->esz();
-    void *d_ones = nullptr, *d_img = nullptr, *d_sh = nullptr;
-    auto cleanup = [&]() { cudaFree(d_ones); cudaFree(d_img); if (where != NFFTB200_DEVICE) cudaFree(d_sh); };
-    CUDA_TRY(p, cudaMalloc(&d_ones, (size_t)std::max<int64_t>(p->M, 1) * csz));
-    if (cudaMalloc(&d_img, (size_t)p->fsz * csz) != cudaSuccess) { cleanup(); return nfftb_fail(p, NFFTB200_OOM, "toeplitz_kernel: out of memory"); }
-    if (where == NFFTB200_DEVICE) d_sh = lambda;
-    else if (cudaMalloc(&d_sh, (size_t)p->fsz * csz) != cudaSuccess) { cleanup(); return nfftb_fail(p, NFFTB200_OOM, "toeplitz_kernel: out of memory"); }
+    // work arrays and the image-sized FFT plan live in the plan (the kernel is often rebuilt for new trajectories)
+    const int64_t need[3] = {std::max<int64_t>(p->M, 1) * (int64_t)csz, p->fsz * (int64_t)csz,
+                             where == NFFTB200_DEVICE ? 0 : p->fsz * (int64_t)csz};
+    for (int i = 0; i < 3; i++) {
+        if (need[i] <= p->cap_toep[i]) continue;
+        if (p->d_toep[i]) { cudaFree(p->d_toep[i]); p->d_toep[i] = nullptr; p->cap_toep[i] = 0; }
+        CUDA_TRY(p, cudaMalloc(&p->d_toep[i], (size_t)need[i]));
+        p->cap_toep[i] = need[i];
+    }
+    if (!p->have_fft_img) {
+        long long n[3];
+        for (int d = 0; d < p->D; d++) n[d] = p->N[p->D - 1 - d];
+        size_t ws = 0;
+        CUFFT_TRY(p, cufftCreate(&p->fft_img));
+        p->have_fft_img = true;
+        CUFFT_TRY(p, cufftMakePlanMany64(p->fft_img, p->D, n, nullptr, 1, p->fsz, nullptr, 1, p->fsz,
+                                         p->dtype == NFFTB200_F32 ? CUFFT_C2C : CUFFT_Z2Z, 1, &ws));
+    }
+    CUFFT_TRY(p, cufftSetStream(p->fft_img, p->stream));
+    void* d_ones = p->d_toep[0];
+    void* d_img = p->d_toep[1];
+    void* d_sh = where == NFFTB200_DEVICE ? lambda : p->d_toep[2];
     if (p->M > 0) {
         if (p->dtype == NFFTB200_F32) k_fill_ones<float2><<<nblk(p->M), 256, 0, p->stream>>>((float2*)d_ones, p->M);
         else k_fill_ones<double2><<<nblk(p->M), 256, 0, p->stream>>>((double2*)d_ones, p->M);
         p->launches++;
     }
-    int st = nfftb200_exec_adjoint(p, d_ones, d_img, NFFTB200_DEVICE);
-    if (st != NFFTB200_OK) { cudaStreamSynchronize(p->stream); cleanup(); return st; }
+    ST_TRY(nfftb200_exec_adjoint(p, d_ones, d_img, NFFTB200_DEVICE));
     Shape3 s;
     for (int d = 0; d < 3; d++) { s.n[d] = (int)p->N[d]; s.o[d] = (int)p->N[d]; }
     if (p->dtype == NFFTB200_F32) k_fftshift<float2><<<nblk(p->fsz), 256, 0, p->stream>>>((const float2*)d_img, (float2*)d_sh, s, p->fsz);
     else k_fftshift<double2><<<nblk(p->fsz), 256, 0, p->stream>>>((const double2*)d_img, (double2*)d_sh, s, p->fsz);
-    p->launches++;
     // fftplan * fftshift(eigMat): unnormalised forward DFT of the image-sized array
-    cufftHandle h = 0;
-    long long n[3];
-    for (int d = 0; d < p->D; d++) n[d] = p->N[p->D - 1 - d];
-    size_t ws = 0;
-    cufftResult r = cufftCreate(&h);
-    if (r == CUFFT_SUCCESS)
-        r = cufftMakePlanMany64(h, p->D, n, nullptr, 1, p->fsz, nullptr, 1, p->fsz,
-                                p->dtype == NFFTB200_F32 ? CUFFT_C2C : CUFFT_Z2Z, 1, &ws);
-    if (r == CUFFT_SUCCESS) r = cufftSetStream(h, p->stream);
-    if (r == CUFFT_SUCCESS)
-        r = p->dtype == NFFTB200_F32 ? cufftExecC2C(h, (cufftComplex*)d_sh, (cufftComplex*)d_sh, CUFFT_FORWARD)
-                                     : cufftExecZ2Z(h, (cufftDoubleComplex*)d_sh, (cufftDoubleComplex*)d_sh, CUFFT_FORWARD);
-    p->launches++;
-    cudaError_t e = cudaSuccess;
-    if (r == CUFFT_SUCCESS && where != NFFTB200_DEVICE)
-        e = cudaMemcpyAsync(lambda, d_sh, (size_t)p->fsz * csz, cudaMemcpyDeviceToHost, p->stream);
-    const cudaError_t e2 = cudaStreamSynchronize(p->stream);
-    if (h) cufftDestroy(h);
-    cleanup();
-    if (r != CUFFT_SUCCESS) return nfftb_fail(p, NFFTB200_CUDA_ERROR, "toeplitz_kernel: cufft error " + std::to_string((int)r));
-    if (e != cudaSuccess || e2 != cudaSuccess)
-        return nfftb_fail(p, NFFTB200_CUDA_ERROR, std::string("toeplitz_kernel: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    if (p->dtype == NFFTB200_F32) CUFFT_TRY(p, cufftExecC2C(p->fft_img, (cufftComplex*)d_sh, (cufftComplex*)d_sh, CUFFT_FORWARD));
+    else CUFFT_TRY(p, cufftExecZ2Z(p->fft_img, (cufftDoubleComplex*)d_sh, (cufftDoubleComplex*)d_sh, CUFFT_FORWARD));
+    p->launches += 2;
+    CUDA_TRY(p, cudaGetLastError());
+    if (where != NFFTB200_DEVICE) {
+        CUDA_TRY(p, cudaMemcpyAsync(lambda, d_sh, (size_t)p->fsz * csz, cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(p, cudaStreamSynchronize(p->stream));
+    }
     return NFFTB200_OK;
 }
 

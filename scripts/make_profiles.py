@@ -36,7 +36,7 @@ with open(os.path.join(out, f"{tag}_kernels.csv"), "w", newline="") as fh:
         traffic[short] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
 if "k_spread_sub3d" in traffic:
     tj = {"source": os.path.basename(rep), "per_kernel_dram_bytes_per_launch": traffic,
-          "spread_dram_bytes_per_launch": traffic.get("k_spread_sub3d", 0) + traffic.get("k_gather_tiles3d", 0)}
+          "spread_dram_bytes_per_launch": traffic.get("k_spread_sub3d", 0) + traffic.get("k_gather_tiles3d", 0) + traffic.get("k_gather_cols3d", 0)}
     json.dump(tj, open(os.path.join(out, "ncu_traffic.json"), "w"), indent=1)
 for kern in sorted(traffic):
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kern}"],
