@@ -219,6 +219,13 @@ template <typename T> inline GeomDev make_geom(const nfftb200_plan* p)
     return g;
 }
 
+// the tiled kernels evaluate only the Kaiser-Bessel window exactly (FULL); the other windows' exact forms (Bessel I0,
+// B-spline recursion, ...) live in the generic kernels so that the hot kernels carry no function call
+inline bool nfftb_tiled_ok(const nfftb200_plan* p)
+{
+    return p->kernel_mode != 1 && !(p->precompute == NFFTB200_FULL && p->window != NFFTB200_KAISER_BESSEL);
+}
+
 template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
 {
     WinDev<T> w;

@@ -411,15 +411,15 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
         explicit KernelTimer(nfftb200_plan* q) : p(q) { if (p->timing) cudaEventRecord(p->evk[3], p->stream); }
         ~KernelTimer() { if (p->timing) { cudaEventRecord(p->evk[4], p->stream); p->pending_k |= 2; } }
     } kt(p);
-    if (p->kernel_mode != 1 && p->D == 1) {
+    if (nfftb_tiled_ok(p) && p->D == 1) {
         const int r = nfftb_interp_1d(p, g, fhat, B, is_complex, i_lo, i_hi);
         if (r >= 0) return r;
     }
-    if (p->kernel_mode != 1 && is_complex && p->D == 2) {
+    if (nfftb_tiled_ok(p) && is_complex && p->D == 2) {
         const int r = nfftb_interp_2d(p, g, fhat, B, t_lo, t_hi);
         if (r >= 0) return r;
     }
-    if (p->kernel_mode != 1 && is_complex && p->D == 3) {
+    if (nfftb_tiled_ok(p) && is_complex && p->D == 3) {
         int r = -1;
         switch (p->m) {
             case 2: r = launch_tile3d<T, 2>(p, g, fhat, B, t_lo, t_hi); break;
@@ -449,7 +449,7 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
 // interpolate the own tile range reading the grid from the ranks' z-slabs; -1 if the tiled kernel does not apply
 int nfftb_peer_interp(nfftb200_plan* p, const SlabTab& st, void* d_fhat, int64_t t_lo, int64_t t_hi)
 {
-    if (p->D != 3) return -1;
+    if (p->D != 3 || (p->precompute == NFFTB200_FULL && p->window != NFFTB200_KAISER_BESSEL)) return -1;
 #define PI_CASE(MM) case MM: return p->dtype == NFFTB200_F32 ? peer_interp<float, MM>(p, st, d_fhat, (int)t_lo, (int)t_hi) \
                                                                : peer_interp<double, MM>(p, st, d_fhat, (int)t_lo, (int)t_hi);
     switch (p->m) {

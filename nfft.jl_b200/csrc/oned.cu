@@ -149,7 +149,7 @@ k_spread_1d(const void* __restrict__ fhat_, void* __restrict__ g_, const T* __re
                         const T v1 = win.lin[a1], v2 = win.lin[a2];
                         w = add_rn(v1, mul_rn(alpha, sub_rn(v2, v1)));
                     } else {
-                        w = win_exact<T>(sub_rn(t, (T)l), MT, win);
+                        w = kb_exact<T>(sub_rn(t, (T)l), MT, win.b);
                     }
                     if constexpr (CPLX) { ax = tfma(w, s_v[x].x, ax); ay = tfma(w, s_v[x].y, ay); }
                     else ax = tfma(w, s_v[x], ax);

@@ -754,7 +754,7 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
                 long long i_lo, long long i_hi)
 {
     const size_t cell = is_complex ? 2 * sizeof(T) : sizeof(T);
-    if (p->kernel_mode != 1 && p->D == 1) {        // output-stationary 1-D spreader: writes every cell, no memset
+    if (nfftb_tiled_ok(p) && p->D == 1) {        // output-stationary 1-D spreader: writes every cell, no memset
         if (p->timing) { cudaEventRecord(p->evk[0], p->stream); cudaEventRecord(p->evk[1], p->stream); }
         const int r = nfftb_spread_1d(p, fhat, g, B, is_complex, t_lo, t_hi);
         if (r >= 0) {
@@ -762,7 +762,7 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
             return r;
         }
     }
-    if (i_hi > i_lo && p->kernel_mode != 1 && is_complex && p->D == 2) {
+    if (i_hi > i_lo && nfftb_tiled_ok(p) && is_complex && p->D == 2) {
         if (p->timing) { cudaEventRecord(p->evk[0], p->stream); cudaEventRecord(p->evk[1], p->stream); }
         const int r = nfftb_spread_2d(p, fhat, g, B, t_lo, t_hi);
         if (r >= 0) {
@@ -770,7 +770,7 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
             return r;
         }
     }
-    if (i_hi > i_lo && p->kernel_mode != 1 && is_complex && p->D == 3) {
+    if (i_hi > i_lo && nfftb_tiled_ok(p) && is_complex && p->D == 3) {
         int r = -1;
         switch (p->m) {
             case 2: r = launch_tile3d<T, 2>(p, fhat, g, B, t_lo, t_hi); break;
@@ -835,7 +835,7 @@ size_t nfftb_spread3d_smem(int dtype, int m, const int64_t* bs)
 // cells of one padded tile sub-grid if the scratch + column-gather spreader applies to this plan, else 0
 int nfftb_peer_tile_cells(nfftb200_plan* p)
 {
-    if (p->D != 3) return 0;
+    if (p->D != 3 || (p->precompute == NFFTB200_FULL && p->window != NFFTB200_KAISER_BESSEL)) return 0;
     PEER_DISPATCH(peer_cells, p)
     return 0;
 }

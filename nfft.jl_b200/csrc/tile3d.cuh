@@ -75,7 +75,7 @@ __device__ __forceinline__ void eval_taps(const WinDev<T>& win, const PolyParam<
         }
     } else {
 #pragma unroll
-        for (int l = 0; l < L; l++) w[l] = win_exact<T>(sub_rn(d0, (T)l), MT, win);
+        for (int l = 0; l < L; l++) w[l] = kb_exact<T>(sub_rn(d0, (T)l), MT, win.b);   // other windows: generic kernels (nfftb_tiled_ok)
     }
 }
 

@@ -608,5 +608,5 @@ def test_copy_gives_independent_plan(nb):
     p.destroy()
     fh = O.random_complex(500, np.float64, 83)
     qa = q.adjoint().copy()
-    assert np.array_equal(qa * fh, q.adjoint() * fh)
+    assert rel(qa * fh, q.adjoint() * fh) < 1e-14           # small 2-D plans spread with global REDs: order may differ
     assert "Adjoint of B200NFFTPlan with 500 sampling points" in repr(qa)
