@@ -98,11 +98,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     from oracle.cpu_ref import CpuRefPlan, lib      # the reference arm is the one place that executes oracle/
     w = WORKLOAD
+    lib().ref_set_num_threads(host_cores())         # torchrun sets OMP_NUM_THREADS=1: use every core we may run on
     cores = lib().ref_num_threads()
     k = random_nodes(w["M"], 3, w["T"], seed=1)
     t0 = time.perf_counter()
@@ -311,6 +319,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_ref import CpuRefPlan, lib
+        lib().ref_set_num_threads(host_cores())
         cores = lib().ref_num_threads()
         pc = CpuRefPlan(k, N, m=w["m"], sigma=w["sigma"], workers=cores)
         pc.forward(f_h); pc.adjoint(fh_h)

@@ -34,6 +34,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.ref_num_threads.restype = C.c_int
+        _LIB.ref_set_num_threads.argtypes = [C.c_int]
     return _LIB
 
 

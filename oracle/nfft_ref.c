@@ -37,6 +37,17 @@
 #undef REAL_EPS
 #undef FMA
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the baseline is meant to use all host cores */
+void ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ref_num_threads(void)
 {
     int n = 1;
