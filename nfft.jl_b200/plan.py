@@ -123,6 +123,51 @@ def _fortran_strides(shape):
     return tuple(s)
 
 
+def _normalise_dims(dims, D):
+    """dims kwarg of plan_nfft (an Integer or a UnitRange, src/precomputation.jl:36-50) -> tuple of 1-based ints"""
+    if dims is None:
+        return tuple(range(1, D + 1))
+    if isinstance(dims, (int, np.integer)):
+        dims = (int(dims),)
+    dims = tuple(int(d) for d in dims)
+    if not dims or dims != tuple(range(dims[0], dims[-1] + 1)) or dims[0] < 1 or dims[-1] > D:
+        raise ArgumentError(f"dims = {dims} must be a range inside 1:{D}")
+    return dims
+
+
+def _dir_to_internal(x, npre, nlead):
+    """directional layout -> batched layout: array of size (pre..., lead..., post...) -> (lead..., B) with the batch
+    index running over (pre..., post...) in column-major order (pre fastest).  numpy or torch; returns a
+    Fortran-ordered array (a copy unless the data already lies that way)."""
+    nd = len(x.shape)
+    order = list(range(npre, npre + nlead)) + list(range(npre)) + list(range(npre + nlead, nd))
+    lead = tuple(x.shape[a] for a in order[:nlead])
+    B = 1
+    for a in order[nlead:]:
+        B *= int(x.shape[a])
+    if _is_torch(x):
+        xr = x.permute(*order[::-1]).contiguous()              # C-contiguous over the reversed dims == column-major
+        return xr.view((B,) + lead[::-1]).permute(*range(nlead, -1, -1))
+    return np.asfortranarray(np.reshape(np.transpose(x, order), lead + (B,), order="F"))
+
+
+def _dir_from_internal(y, pre, post, out):
+    """inverse of _dir_to_internal: y of size (lead..., B) is written into out of size (pre..., lead..., post...)"""
+    nlead = len(y.shape) - 1
+    npre = len(pre)
+    lead = tuple(y.shape[:nlead])
+    nd = npre + nlead + len(post)
+    order = list(range(npre, npre + nlead)) + list(range(npre)) + list(range(npre + nlead, nd))
+    inv = [order.index(a) for a in range(nd)]
+    full = lead + tuple(pre) + tuple(post)
+    if _is_torch(y):
+        yr = y.permute(*range(nlead, -1, -1)).contiguous().view(full[::-1]).permute(*range(nd - 1, -1, -1))
+        out.copy_(yr.permute(*inv))
+    else:
+        out[...] = np.transpose(np.reshape(y, full, order="F"), inv)
+    return out
+
+
 class _Buf:
     """pointer + location of a caller array; keeps converted copies alive"""
 
@@ -144,15 +189,22 @@ class B200NFFTPlan:
             N = (int(N),)
         N = tuple(int(n) for n in N)
         D = len(N)
-        if dims is not None and tuple(dims) != tuple(range(1, D + 1)):
-            # directional plan (src/directional.jl, test/accuracy.jl:123-163): a transform over the LEADING dims
-            # 1:D-1 of an (N..., B) array is exactly a batched plan with ntransforms = B (batch slowest)
-            if tuple(dims) == tuple(range(1, D)) and D >= 2 and int(ntransforms) == 1:
-                ntransforms = N[-1]
-                N = N[:-1]
-                D -= 1
-            else:
-                raise NotImplementedError("GPU NFFT does not work along directions right now!")  # ext/...:35-37
+        dims_t = _normalise_dims(dims, D)
+        self._dir = None
+        self._user_N = N
+        if dims_t != tuple(range(1, D + 1)):
+            # directional plan (src/directional.jl, test/accuracy.jl:83-163): the transform runs over dims of an
+            # array of size N, every other dimension is a batch.  A transform over the LEADING dims 1:D-1 is exactly
+            # a batched plan with ntransforms = N[D] (batch slowest, no copies); any other dims are brought to that
+            # layout by one permuting copy on the way in and one on the way out (_dir_to_internal/_from_internal).
+            if int(ntransforms) != 1:
+                raise ArgumentError("a directional plan (dims=...) cannot also be batched (ntransforms > 1)")
+            pre, post = N[:dims_t[0] - 1], N[dims_t[-1]:]
+            if not (len(pre) == 0 and len(post) == 1):
+                self._dir = (tuple(pre), tuple(post))
+            ntransforms = int(np.prod(pre + post))
+            N = N[dims_t[0] - 1:dims_t[-1]]
+            D = len(N)
         window = str(window).lstrip(":")
         if window not in WINDOWS:
             raise NotImplementedError(f"Window {window} not yet implemented!")      # src/windowFunctions.jl:16
@@ -178,7 +230,7 @@ class B200NFFTPlan:
         self.device = int(device)
         self.N = N
         self.D = D
-        self.dims = range(1, D + 1)
+        self.dims = range(dims_t[0], dims_t[-1] + 1)
         # ---- multi-GPU (one process per GPU): shard = None | "batch" | "nodes"
         self.shard = shard
         self.rank, self.world = 0, 1
@@ -262,10 +314,31 @@ class B200NFFTPlan:
 
     # ---- interface.jl:170-211 -----------------------------------------------------------------
     def size_in(self):
-        return self._bshape(self.N)
+        return self._user_shape(self.N)
 
     def size_out(self):
-        return self._bshape(self.NOut)
+        return self._user_shape(self.NOut)
+
+    def _user_shape(self, lead):
+        """shape the caller sees: (lead..., B) for batched plans, (pre..., lead..., post...) for directional ones"""
+        if self._dir is None:
+            return self._bshape(lead)
+        return self._dir[0] + tuple(lead) + self._dir[1]
+
+    def _dir_call(self, fn, out, x, lead_out, lead_in, **kw):
+        """run a batched transform on directional data: permute in, transform, permute out"""
+        if tuple(x.shape) != self._user_shape(lead_in) or tuple(out.shape) != self._user_shape(lead_out):
+            raise DimensionMismatch("Data is not consistent with NFFTPlan")
+        dev = _is_torch(x) and x.is_cuda
+        if dev != (_is_torch(out) and out.is_cuda):
+            raise ArgumentError("input and output must both be host (numpy) or both device (CUDA tensor) arrays")
+        xi = _dir_to_internal(x if (dev or not _is_torch(x)) else x.numpy(), len(self._dir[0]), len(lead_in))
+        if not dev:
+            xi = np.asfortranarray(xi, dtype=self.cT)
+        yi = _empty_fortran(self._bshape(lead_out), self.cT, self.device, dev)
+        fn(yi, xi, _internal=True, **kw)
+        _dir_from_internal(yi, self._dir[0], self._dir[1], out)
+        return out
 
     def adjoint(self):
         return AdjointPlan(self)
@@ -448,7 +521,11 @@ class B200NFFTPlan:
         self._async_keep += [bi.keep, bo.keep]
         return HOST_ASYNC
 
-    def mul_forward(self, fHat, f, timing=None, verbose=False, async_host=False):
+    def mul_forward(self, fHat, f, timing=None, verbose=False, async_host=False, _internal=False):
+        if self._dir is not None and not _internal:
+            if async_host:
+                raise ArgumentError("async_host is not available for plans that permute their data (dims=...)")
+            return self._dir_call(self.mul_forward, fHat, f, self.NOut, self.N, timing=timing, verbose=verbose)
         # consistencyCheck, src/utils.jl:98-105
         if tuple(f.shape) != self._bshape(self.N) or tuple(fHat.shape) != self._bshape(self.NOut):
             raise DimensionMismatch("Data is not consistent with NFFTPlan")
@@ -466,7 +543,11 @@ class B200NFFTPlan:
             print(f"Timing: deconv={timing.deconv} fft={timing.fft} conv={timing.conv}")
         return fHat
 
-    def mul_adjoint(self, f, fHat, timing=None, verbose=False, async_host=False):
+    def mul_adjoint(self, f, fHat, timing=None, verbose=False, async_host=False, _internal=False):
+        if self._dir is not None and not _internal:
+            if async_host:
+                raise ArgumentError("async_host is not available for plans that permute their data (dims=...)")
+            return self._dir_call(self.mul_adjoint, f, fHat, self.N, self.NOut, timing=timing, verbose=verbose)
         if tuple(f.shape) != self._bshape(self.N) or tuple(fHat.shape) != self._bshape(self.NOut):
             raise DimensionMismatch("Data is not consistent with NFFTPlan")
         self._timing(timing)
@@ -492,7 +573,7 @@ class B200NFFTPlan:
     # allocating versions, derived.jl:174-208
     def __mul__(self, f):
         dev = _is_torch(f) and f.is_cuda
-        out = self.empty_out(device=dev, batch=True)
+        out = _empty_fortran(self.size_out(), self.cT, self.device, dev)
         return self.mul_forward(out, f)
 
     __matmul__ = __mul__
@@ -593,7 +674,7 @@ class AdjointPlan:
     def __mul__(self, fHat):
         p = self.parent
         dev = _is_torch(fHat) and fHat.is_cuda
-        out = p.empty_image(device=dev, batch=True)
+        out = _empty_fortran(p.size_in(), p.cT, p.device, dev)
         return p.mul_adjoint(out, fHat)
 
     __matmul__ = __mul__

@@ -610,3 +610,40 @@ def test_copy_gives_independent_plan(nb):
     qa = q.adjoint().copy()
     assert rel(qa * fh, q.adjoint() * fh) < 1e-14           # small 2-D plans spread with global REDs: order may differ
     assert "Adjoint of B200NFFTPlan with 500 sampling points" in repr(qa)
+
+
+@pytest.mark.parametrize("N", [(8, 12), (10, 8, 14)])
+def test_directional_plans_any_dims(nb, N):
+    """test/accuracy.jl:83-163: an NFFT along dims=d (or dims=d:d+1) equals the lower-dimensional NFFT of every slice
+    along those dims, for every position of the transformed dims (leading, middle, trailing), numpy and CUDA buffers"""
+    import itertools
+    import torch
+    D, T = len(N), np.float64
+    J = 60
+    cases = [(d,) for d in range(1, D + 1)] + ([(d, d + 1) for d in range(1, D)] if D == 3 else [])
+    for dims in cases:
+        nd = len(dims)
+        k = O.random_nodes(J, nd, T, seed=90 + dims[0])
+        f = O.random_complex(N, T, 91)
+        p_dir = nb.plan_nfft(k.T if nd > 1 else k[:, 0], N, dims=dims if nd > 1 else dims[0], m=5, σ=2.0)
+        pre, post = N[:dims[0] - 1], N[dims[-1]:]
+        assert p_dir.size_in() == tuple(N) and p_dir.size_out() == pre + (J,) + post
+        fHat_dir = p_dir * f
+        g_dir = p_dir.adjoint() * fHat_dir
+        p = nb.plan_nfft(k.T, N[dims[0] - 1:dims[-1]], m=5, σ=2.0)
+        fHat = np.zeros_like(fHat_dir)
+        g = np.zeros_like(g_dir)
+        for Ipost in itertools.product(*[range(n) for n in post]):
+            for Ipre in itertools.product(*[range(n) for n in pre]):
+                idxf = Ipre + (slice(None),) * nd + Ipost
+                idxh = Ipre + (slice(None),) + Ipost
+                fHat[idxh] = p * np.asfortranarray(f[idxf])
+                g[idxf] = p.adjoint() * np.ascontiguousarray(fHat_dir[idxh])
+        assert rel(fHat_dir, fHat) < 1e-13 and rel(g_dir, g) < 1e-13
+        # device buffers
+        fd = torch.from_numpy(np.ascontiguousarray(f)).cuda()
+        hd = p_dir * fd
+        assert hd.is_cuda and rel(hd.cpu().numpy(), fHat) < 1e-13
+        assert rel((p_dir.adjoint() * hd).cpu().numpy(), g) < 1e-13
+    with pytest.raises(nb.ArgumentError):
+        nb.plan_nfft(O.random_nodes(J, 1, T, seed=1)[:, 0], N, dims=1, ntransforms=2, m=5, σ=2.0)
