@@ -473,8 +473,8 @@ def test_sdc_function_and_directional_plan(nb):
     p2 = O.OraclePlan(k, N3[:2], m=5, sigma=2.0, blockSize=pd.params.blockSize)
     for b in range(5):
         assert rel(out[:, b], p2.forward(np.asfortranarray(f[..., b]))) < 1e-12
-    with pytest.raises(NotImplementedError):
-        nb.plan_nfft(k.T, N3, dims=range(2, 4))
+    with pytest.raises(nb.ArgumentError):
+        nb.plan_nfft(k.T, N3, dims=(1, 3))                     # not a range
 
 
 def test_multi_gpu_node_and_batch_sharding():
