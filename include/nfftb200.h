@@ -176,6 +176,13 @@ int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, i
  * bit 1: the forward interpolates straight from the ranks' z-slabs over peer memory instead of ncclAllGather */
 int nfftb200_comm_is_fused(nfftb200_plan* p);
 
+/* ---- sampling density compensation ------------------------------------------------------------------
+ * NFFTTools.sdc(p; iters) (NFFTTools/src/samplingDensity.jl:59-155): `iters` Pipe-Menon iterations on real data
+ * through convolve_transpose!/convolve!, then the global scaling c = real(sum v)/sum|v|^2, v = A' D(w) A 1.
+ * Everything runs on the device; weights receives M values of T (host or device).  Plan with ntransforms = 1.
+ * Returns NFFTB200_BAD_ARGUMENT with "non-positive weights" where the reference throws that string. */
+int nfftb200_sdc(nfftb200_plan* p, int iters, void* weights, int where);
+
 /* ---- Toeplitz (Gram) operator, the iterative-reconstruction caller either side of the path --------------
  * nfftb200_toeplitz_kernel: calculateToeplitzKernel!(f, p, tr, fftplan) after its nodes!(p, tr)
  * (NFFTTools/src/Toeplitz.jl:131-137, and :86-93): lambda = FFT(fftshift(adjoint(p) * ones)).  The plan's image

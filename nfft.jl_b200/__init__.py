@@ -7,12 +7,13 @@ from ._lib import LIB_PATH, SYMBOLS, build, lib
 from .plan import (FULL, LINEAR, POLYNOMIAL, TENSOR, AdjointPlan, ArgumentError, B200NFFTPlan,
                    DimensionMismatch, NFFTParams, PrecomputeFlags, TimingStats, accuracyParams, adjoint,
                    convolve_, convolve_transpose_, deconvolve_, deconvolve_transpose_, mul_, nfft,
-                   nfft_adjoint, nodes_, partition_tiles, plan_nfft, sdc, shard_batch, size_in, size_out)
+                   nfft_adjoint, nodes_, partition_tiles, plan_nfft, sdc, sdc_host_loop, shard_batch, size_in,
+                   size_out)
 from .toeplitz import (ToeplitzOperator, calculateToeplitzKernel, calculateToeplitzKernel_,
                        convolveToeplitzKernel_)
 
 __all__ = ["calculateToeplitzKernel", "calculateToeplitzKernel_", "convolveToeplitzKernel_", "ToeplitzOperator",
            "plan_nfft", "nodes_", "mul_", "adjoint", "size_in", "size_out", "convolve_", "convolve_transpose_",
-           "deconvolve_", "deconvolve_transpose_", "nfft", "nfft_adjoint", "sdc", "PrecomputeFlags", "FULL", "TENSOR",
+           "deconvolve_", "deconvolve_transpose_", "nfft", "nfft_adjoint", "sdc", "sdc_host_loop", "PrecomputeFlags", "FULL", "TENSOR",
            "LINEAR", "POLYNOMIAL", "TimingStats", "NFFTParams", "B200NFFTPlan", "AdjointPlan", "ArgumentError",
            "DimensionMismatch", "accuracyParams", "shard_batch", "partition_tiles", "build", "lib", "LIB_PATH", "SYMBOLS"]

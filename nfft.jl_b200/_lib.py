@@ -18,7 +18,7 @@ SYMBOLS = [
     "nfftb200_get_timing", "nfftb200_get_kernel_times", "nfftb200_set_kernel_mode", "nfftb200_get_launch_count", "nfftb200_set_stream",
     "nfftb200_sync", "nfftb200_comm_unique_id", "nfftb200_partition_tiles", "nfftb200_comm_init", "nfftb200_comm_is_fused", "nfftb200_last_error",
     "nfftb200_status_string", "nfftb200_version",
-    "nfftb200_toeplitz_kernel", "nfftb200_toeplitz_create", "nfftb200_toeplitz_set_kernel", "nfftb200_toeplitz_apply",
+    "nfftb200_sdc", "nfftb200_toeplitz_kernel", "nfftb200_toeplitz_create", "nfftb200_toeplitz_set_kernel", "nfftb200_toeplitz_apply",
     "nfftb200_toeplitz_set_stream", "nfftb200_toeplitz_sync", "nfftb200_toeplitz_destroy", "nfftb200_toeplitz_last_error",
 ]
 
@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
         L.nfftb200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.nfftb200_comm_is_fused.argtypes = [C.c_void_p]
         L.nfftb200_accuracy_params.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.nfftb200_sdc.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.nfftb200_toeplitz_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.nfftb200_toeplitz_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.nfftb200_toeplitz_set_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_int]

@@ -735,9 +735,28 @@ def deconvolve_transpose_(p, g, f):
     return p.deconvolve_transpose_(g, f)
 
 
-def sdc(p, iters=20):
+def sdc(p, iters=20, device=False):
     """NFFTTools.sdc (NFFTTools/src/samplingDensity.jl:59-155): Pipe-Menon density compensation weights through
-    the real-valued convolve_transpose!/convolve! pair, followed by the least-squares global scaling."""
+    the real-valued convolve_transpose!/convolve! pair, followed by the least-squares global scaling.  The whole
+    iteration runs inside the library on the device (nfftb200_sdc); the result is a numpy vector, or a CUDA tensor
+    with device=True."""
+    if device:
+        w = torch.empty(p.J, dtype=_torch_dtype(p.T), device=f"cuda:{p.device}")
+        _check(p._h, p._L.nfftb200_sdc(p._h, int(iters), C.c_void_p(w.data_ptr()), DEVICE))
+        return w
+    w = np.empty(p.J, dtype=p.T)
+    try:
+        _check(p._h, p._L.nfftb200_sdc(p._h, int(iters), C.c_void_p(w.ctypes.data), HOST))
+    except ArgumentError as e:
+        if "non-positive weights" in str(e):
+            raise ValueError("non-positive weights") from e       # the reference throws this string
+        raise
+    return w
+
+
+def sdc_host_loop(p, iters=20):
+    """The same algorithm written against the public operators (host work buffers), as NFFTTools does it for any
+    AbstractNFFTPlan; kept as the cross-check of the native path."""
     T, J = p.T, p.J
     weights = np.ones(J, dtype=T)
     tmp = np.empty(J, dtype=T)

@@ -647,3 +647,29 @@ def test_directional_plans_any_dims(nb, N):
         assert rel((p_dir.adjoint() * hd).cpu().numpy(), g) < 1e-13
     with pytest.raises(nb.ArgumentError):
         nb.plan_nfft(O.random_nodes(J, 1, T, seed=1)[:, 0], N, dims=1, ntransforms=2, m=5, σ=2.0)
+
+
+@pytest.mark.parametrize("D,T", [(1, np.float64), (2, np.float32), (2, np.float64), (3, np.float32)])
+def test_native_sdc_matches_operator_loop(nb, D, T):
+    """nfftb200_sdc (the whole Pipe-Menon iteration + scaling on the device) against the same algorithm written with
+    the public operators as NFFTTools does (NFFTTools/src/samplingDensity.jl:93-155) and against the oracle, on a
+    radial-like non-uniform node set; device output variant"""
+    N = {1: (64,), 2: (24, 20), 3: (12, 10, 8)}[D]
+    rng = np.random.default_rng(5)
+    M = 4 * int(np.prod(N))
+    r = rng.random(M) ** 1.5 * 0.5                        # denser near the centre
+    d = rng.standard_normal((M, D)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = (r[:, None] * d).astype(T)
+    p = nb.plan_nfft(k.T, N, m=4, σ=2.0)
+    w = nb.sdc(p, iters=12)
+    assert w.dtype == T and w.shape == (M,) and np.all(w > 0)
+    w_loop = nb.sdc_host_loop(p, iters=12)
+    tol = 2e-4 if T == np.float32 else 1e-10
+    assert np.abs(w / w_loop - 1).max() < tol
+    po = O.OraclePlan(k, N, m=4, sigma=2.0, blockSize=p.params.blockSize)
+    assert np.abs(w / O.sdc(po, iters=12) - 1).max() < (1e-3 if T == np.float32 else 1e-9)
+    wd = nb.sdc(p, iters=12, device=True)
+    assert wd.is_cuda and np.abs(wd.cpu().numpy() / w - 1).max() < tol
+    pb = nb.plan_nfft(k.T, N, m=4, σ=2.0, ntransforms=2)
+    with pytest.raises(NotImplementedError):
+        nb.sdc(pb)
