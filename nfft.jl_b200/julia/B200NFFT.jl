@@ -215,6 +215,15 @@ end
 Base.copy(p::B200NFFTPlan{T,D}) where {T,D} =
     B200NFFTPlan(p.k, p.N; m=p.m, σ=p.σ, precompute=p.precompute, ntransforms=p.ntransforms)
 
+# ---- sampling density compensation, NFFTTools/src/samplingDensity.jl:59-155 ---------------------------------
+"sdc(p; iters=20): Pipe-Menon weights, all iterations on the device (NFFTTools.sdc works too, through convolve!)"
+function sdc(p::B200NFFTPlan{T,D}; iters::Int=20) where {T,D}
+    w = Vector{T}(undef, p.J)
+    check(p.handle, ccall((:nfftb200_sdc, libnfftb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint),
+                          p.handle, iters, w, HOST))
+    return w
+end
+
 # ---- Toeplitz (Gram) operator, NFFTTools/src/Toeplitz.jl ------------------------------------------------------
 "calculateToeplitzKernel!(f, p, tr, fftplan) (NFFTTools/src/Toeplitz.jl:131-137): the FFT plan lives in the library"
 function calculateToeplitzKernel!(f::AbstractArray{Complex{T},D}, p::B200NFFTPlan{T,D}, tr::Matrix{T}, fftplan=nothing) where {T,D}
