@@ -360,10 +360,21 @@ import os as _os
 def test_against_committed_golden_vectors(nb, path):
     """tests/golden/*.npz (oracle-generated, script committed): permutation bit-exact, outputs within tolerance"""
     z = np.load(path)
-    N = tuple(int(n) for n in z["N"])
     k = z["k"]
     T = k.dtype.type
-    p = nb.plan_nfft(k.T, N, m=int(z["m"]), σ=2.0, precompute=nb.PrecomputeFlags(int(z["pre"])),
+    if "toeplitz_lambda" in z:         # NFFTTools fixtures: Toeplitz kernel / apply and sdc
+        shape = tuple(int(n) for n in z["shape"])
+        lam = nb.calculateToeplitzKernel(shape, k.T, m=4, σ=2.0)
+        assert rel(lam, z["toeplitz_lambda"]) < (1e-11 if T == np.float64 else 2e-5)
+        y = np.asfortranarray(z["y"]).copy(order="F")
+        nb.convolveToeplitzKernel_(y, np.asfortranarray(z["toeplitz_lambda"]))
+        assert rel(y, z["toeplitz_out"]) < TOL[T]
+        p = nb.plan_nfft(k.T, shape, m=4, σ=2.0, blockSize=tuple(int(b) for b in z["blockSize"]))
+        assert np.abs(nb.sdc(p, iters=10) / z["sdc"] - 1).max() < (1e-9 if T == np.float64 else 1e-3)
+        return
+    N = tuple(int(n) for n in z["N"])
+    window = str(z["window"]) if "window" in z else "kaiser_bessel"
+    p = nb.plan_nfft(k.T, N, m=int(z["m"]), σ=2.0, precompute=nb.PrecomputeFlags(int(z["pre"])), window=window,
                      blockSize=tuple(int(b) for b in z["blockSize"]))
     assert np.array_equal(p.permutation()[0], z["perm"])
     assert rel(p * z["f"], z["forward"]) < TOL[T]

@@ -257,13 +257,23 @@ def test_golden_fixtures(path):
     """committed vectors (tests/golden/make_golden.py): the oracle must keep reproducing them, and they
     must stay within the reference's tolerance of the NDFT"""
     z = np.load(path)
-    N = tuple(int(n) for n in z["N"])
     k = z["k"]
-    p = O.OraclePlan(k, N, m=int(z["m"]), sigma=2.0, precompute=int(z["pre"]))
-    assert np.array_equal(p.perm, z["perm"])
     tol = 1e-13 if k.dtype == np.float64 else 1e-6
+    if "toeplitz_lambda" in z:         # NFFTTools fixtures: Toeplitz kernel / apply (test/testToeplitz.jl) and sdc
+        shape = tuple(int(n) for n in z["shape"])
+        lam = O.calculate_toeplitz_kernel(shape, k, m=4, sigma=2.0)
+        assert rel(lam, z["toeplitz_lambda"]) < tol
+        assert _approx(z["toeplitz_lambda"], z["toeplitz_explicit"], 1e-6 if k.dtype == np.float64 else 1e-5)
+        assert rel(O.convolve_toeplitz_kernel(z["y"], lam), z["toeplitz_out"]) < 10 * tol
+        p = O.OraclePlan(k, shape, m=4, sigma=2.0)
+        assert np.abs(O.sdc(p, iters=10) / z["sdc"] - 1).max() < (1e-10 if k.dtype == np.float64 else 1e-4)
+        return
+    N = tuple(int(n) for n in z["N"])
+    window = str(z["window"]) if "window" in z else "kaiser_bessel"
+    p = O.OraclePlan(k, N, m=int(z["m"]), sigma=2.0, precompute=int(z["pre"]), window=window)
+    assert np.array_equal(p.perm, z["perm"])
     assert rel(p.forward(z["f"]), z["forward"]) < tol
     assert rel(p.adjoint(z["fHat"]), z["adjoint"]) < tol
-    bar = {3: 3e-5, 4: 1e-6, 5: 1e-7}[int(z["m"])]
+    bar = {3: 3e-5, 4: 1e-6, 5: WINDOW_EPS[window]}[int(z["m"])]
     assert rel(z["forward"], z["ndft"]) < bar
     assert rel(z["adjoint"], z["ndft_adjoint"]) < bar
