@@ -523,7 +523,9 @@ k_gather_tiles3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cp
 // process (CUDA IPC over NVLink), a tile's sub-grid is read from the rank that owns the tile, and only the z layers
 // [tz0, tz0 + gridDim.z) of this rank's slab are produced -- the spread's halo exchange and the reduce-scatter
 // in one pass, with no atomics and a fixed summation order.
-template <typename T, int MT, int BSZ, bool PEER>
+// ZS = 2 splits a column between two threads (half a tile layer each): half the accumulator registers, twice the
+// resident threads to cover the DRAM latency; the per-cell summation order does not change.
+template <typename T, int MT, int BSZ, bool PEER, int ZS>
 __global__ void __launch_bounds__(128)
 k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cplx<T>::type* __restrict__ g,
                 const int32_t* __restrict__ tile_items, int tile_lo, int tile_hi, int item_lo, int item_hi, GeomDev geo,
@@ -537,8 +539,11 @@ k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cpl
     const unsigned PN = (unsigned)plane * PZ;
     const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const int u1 = blockIdx.y;
-    const int tzc = PEER ? (int)blockIdx.z + tz0 : (int)(blockIdx.z % geo.nb[2]);
-    const int b = PEER ? 0 : (int)(blockIdx.z / geo.nb[2]);
+    constexpr int HZ = BSZ / ZS;                           // planes per thread
+    static_assert(BSZ % ZS == 0 && HZ >= MT, "half layers must hold a halo");
+    const int zh = (int)(blockIdx.z % ZS), zl = (int)(blockIdx.z / ZS);
+    const int tzc = PEER ? zl + tz0 : zl % geo.nb[2];
+    const int b = PEER ? 0 : zl / geo.nb[2];
     if (u0 >= geo.Nt[0]) return;
     if (!PEER) scratch += (size_t)b * (size_t)(item_hi - item_lo) * PN;
     auto cover = [&](int u, int d, int tmul, int pmul, int (&tt)[3], int (&po)[3]) -> int {
@@ -570,9 +575,9 @@ k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cpl
     // z layers: own, below (its high halo covers my planes [0,m)), above (its low halo covers [BSZ-m, BSZ))
     const int nb2 = geo.nb[2], tmz = geo.nb[0] * geo.nb[1];
     const int tzp = tzc == 0 ? nb2 - 1 : tzc - 1, tzn = tzc == nb2 - 1 ? 0 : tzc + 1;
-    T ax0[BSZ], ay0[BSZ], ax1[BSZ], ay1[BSZ];
+    T ax0[HZ], ay0[HZ], ax1[HZ], ay1[HZ];
 #pragma unroll
-    for (int k = 0; k < BSZ; k++) { ax0[k] = ay0[k] = ax1[k] = ay1[k] = 0; }
+    for (int k = 0; k < HZ; k++) { ax0[k] = ay0[k] = ax1[k] = ay1[k] = 0; }
     for (int iy = 0; iy < ny; iy++)
         for (int ix = 0; ix < nx; ix++) {
             const int txy = ty[iy] + xt[ix];
@@ -599,14 +604,14 @@ k_gather_cols3d(const typename Cplx<T>::type* __restrict__ scratch, typename Cpl
                     }
                 }
             };
-            add_layer(tzc, std::integral_constant<int, 0>{}, std::integral_constant<int, BSZ>{}, MT);
-            add_layer(tzp, std::integral_constant<int, 0>{}, std::integral_constant<int, MT>{}, MT + BSZ);
-            add_layer(tzn, std::integral_constant<int, BSZ - MT>{}, std::integral_constant<int, MT>{}, 0);
+            add_layer(tzc, std::integral_constant<int, 0>{}, std::integral_constant<int, HZ>{}, MT + zh * HZ);
+            if (zh == 0) add_layer(tzp, std::integral_constant<int, 0>{}, std::integral_constant<int, MT>{}, MT + BSZ);
+            if (zh == ZS - 1) add_layer(tzn, std::integral_constant<int, HZ - MT>{}, std::integral_constant<int, MT>{}, 0);
         }
-    C* dst = g + (size_t)b * geo.gsz + ((size_t)((tzc - (PEER ? tz0 : 0)) * BSZ) * geo.Nt[1] + u1) * geo.Nt[0] + u0;
+    C* dst = g + (size_t)b * geo.gsz + ((size_t)((tzc - (PEER ? tz0 : 0)) * BSZ + zh * HZ) * geo.Nt[1] + u1) * geo.Nt[0] + u0;
     const size_t gplane = (size_t)geo.Nt[0] * geo.Nt[1];
 #pragma unroll
-    for (int k = 0; k < BSZ; k++) {
+    for (int k = 0; k < HZ; k++) {
         if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst + k * gplane) = make_float4((float)ax0[k], (float)ay0[k], (float)ax1[k], (float)ay1[k]);
         else { dst[k * gplane] = make_c<T>(ax0[k], ay0[k]); dst[k * gplane + 1] = make_c<T>(ax1[k], ay1[k]); }
     }
@@ -661,8 +666,8 @@ int launch_tile3d_nw(nfftb200_plan* p, const void* fhat, void* g, int B, int t_l
         int bx = 32;
         if (p->kernel_mode != 5 && geo.bs[2] == 16 && geo.Nt[2] % 16 == 0 && 16 >= 2 * MT) {
             while (bx < 128 && bx < units) bx <<= 1;
-            dim3 gc((units + bx - 1) / bx, geo.Nt[1], geo.nb[2] * B);
-            k_gather_cols3d<T, MT, 16, false><<<gc, bx, 0, st>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo, PeerTab{}, 0);
+            dim3 gc((units + bx - 1) / bx, geo.Nt[1], geo.nb[2] * B * 2);
+            k_gather_cols3d<T, MT, 16, false, 2><<<gc, bx, 0, st>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo, PeerTab{}, 0);
             p->launches += 2;
             CUDA_TRY(p, cudaGetLastError());
             return NFFTB200_OK;
@@ -731,8 +736,8 @@ int peer_gather(nfftb200_plan* p, void* slab, int layer_lo, int nlayers, const P
     const int units = geo.Nt[0] / 2;
     int bx = 32;
     while (bx < 128 && bx < units) bx <<= 1;
-    dim3 gc((units + bx - 1) / bx, geo.Nt[1], nlayers);
-    k_gather_cols3d<T, MT, 16, true><<<gc, bx, 0, p->stream>>>(nullptr, (C*)slab, p->d_tile_items, 0, 0, 0, 0, geo, pt, layer_lo);
+    dim3 gc((units + bx - 1) / bx, geo.Nt[1], nlayers * 2);
+    k_gather_cols3d<T, MT, 16, true, 2><<<gc, bx, 0, p->stream>>>(nullptr, (C*)slab, p->d_tile_items, 0, 0, 0, 0, geo, pt, layer_lo);
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;
