@@ -337,7 +337,7 @@ class B200NFFTPlan:
             xi = np.asfortranarray(xi, dtype=self.cT)
         yi = _empty_fortran(self._bshape(lead_out), self.cT, self.device, dev)
         fn(yi, xi, _internal=True, **kw)
-        _dir_from_internal(yi, self._dir[0], self._dir[1], out)
+        _dir_from_internal(yi, self._dir[0], self._dir[1], out.numpy() if (_is_torch(out) and not dev) else out)
         return out
 
     def adjoint(self):
