@@ -1,0 +1,395 @@
+// spread_bin.cuh -- K3 variant "register footprint" (kernel_mode 7, opt-in): adjoint gridding of one reference tile
+//   replaces fillBlock!/fillOneNode! (/root/reference/src/convolution.jl:445-492) like k_spread_sub3d, and hands the
+//   same padded tile ("blocks[l]") to the same gather pass (addBlock!, :371-443).
+//
+// Why: k_spread_sub3d read-modify-writes (2m)^3 complex cells of shared memory per node, so its accumulate loop is
+// bound by the 128 B/clk shared-memory pipe.  Here the footprints of SEVERAL nodes are summed in
+// REGISTERS first and shared memory sees one read-modify-write per bin:
+//   * the nodes of the tile (already contiguous after the plan-time sort) are counting-sorted inside the CTA into
+//     bins of G^3 consecutive first-tap positions, G = W - 2m + 1, so that every node of a bin has its (2m)^3 taps
+//     inside one W^3 window (W = 8 for m <= 3);
+//   * one warp accumulates one bin: lane r owns the x-row (y, z) = (r % W, r / W) of the window (W complex
+//     accumulators per pass, ceil(W*W/32) passes), the node's weights are laid out on the window (zeros outside
+//     the node's taps) so the inner loop is W*2 FFMA per pass and node with no address arithmetic;
+//   * bins whose windows are disjoint run concurrently: bins are coloured by (index mod S) per dimension,
+//     S = ceil(W/G), and the S^3 colours are separated by CTA barriers, so no atomics are needed and the
+//     summation order is fixed (bit-reproducible, as in the default kernel);
+//   * window weights of a bin are evaluated 8 nodes at a time, lane = (node, dimension), with the constant-bank
+//     Horner of tile3d.cuh.
+// FFMA work grows by W^3/(2m)^3 (2.4x for m = 3), shared-memory traffic per node falls from 2*(2m)^3 cells to
+// 2*W^3/(nodes per bin) plus 5 broadcast loads.  One padded tile instead of 8 private sub-tiles: 107 KB for
+// Float32, two CTAs per SM.
+//
+// The file holds device code only and is also compiled for the HOST by tests/emu (one OS thread per CUDA thread),
+// which checks the kernel's indexing against a direct evaluation without a GPU.
+#pragma once
+#include "common.cuh"
+#include "window.cuh"
+#include "tile3d.cuh"
+
+// alignment checks of the vector accesses: active only in the host emulation build (tests/emu defines it)
+#ifndef NFFTB_EMU_ALIGNED
+#define NFFTB_EMU_ALIGNED(ptr, bytes)
+#endif
+
+#define NFFTB_BIN_MAXKEYS 256
+#define NFFTB_BIN_WARPS 8
+#define NFFTB_BIN_ROUND 8          // nodes whose weights are evaluated together (lane = node * 3 + dim)
+
+template <typename T> struct BinChunk { static constexpr int value = sizeof(T) == 4 ? 640 : 512; };
+
+struct BinGeom {
+    int G;             // first-tap positions per bin and dimension
+    int S;             // colour stride in bins: windows of bins i and i + S are disjoint
+    int nbin[3];       // bins per dimension = ceil(bs / G)
+    int nkeys;         // nbin[0] * nbin[1] * nbin[2]  (<= NFFTB_BIN_MAXKEYS)
+    int PXp, PL;       // row pitch / plane pitch of the padded tile in shared memory (cells), bank-conflict free
+    int PNs;           // cells of the shared-memory tile (PL * PZ, even)
+};
+
+// bank-conflict degree of the read-modify-write of one pass: lane r touches cell (z*PL + y*PXp + i), i uniform
+inline int bin_conflict_degree(int W, int cell_bytes, int PXp, int PL)
+{
+    const int group = 128 / cell_bytes;                   // lanes served by one wavefront (16 for 8 B, 8 for 16 B)
+    const int wpc = cell_bytes / 4;                       // banks per cell
+    int worst = 1;
+    const int rows = W * W, passes = (rows + 31) / 32;
+    for (int p = 0; p < passes; p++)
+        for (int g0 = 0; g0 < 32; g0 += group) {
+            int cnt[32] = {0};
+            for (int l = g0; l < g0 + group; l++) {
+                const int r = l + 32 * p;
+                if (r >= rows) continue;
+                const long long cell = (long long)(r / W) * PL + (long long)(r % W) * PXp;
+                const int bank = (int)((cell * wpc) % 32);
+                cnt[bank]++;
+            }
+            for (int b = 0; b < 32; b++) worst = cnt[b] > worst ? cnt[b] : worst;
+        }
+    return worst;
+}
+
+template <typename T, int MT, int W> struct BinLayout {
+    using C = typename Cplx<T>::type;
+    static constexpr int L = 2 * MT;
+    static constexpr int G = W - L + 1;
+    static constexpr int RW = 4 * W;                       // record: wx[W] | wy[W] | (wz * v)[W] interleaved re, im
+    static constexpr int ROWS = W * W, NP = (ROWS + 31) / 32;
+    static_assert(G >= 1, "window narrower than the footprint");
+
+    // returns false if the tile cannot be binned (too many bins)
+    static bool make(const int* bs, BinGeom& bg)
+    {
+        bg.G = G;
+        bg.S = (W + G - 1) / G;
+        bg.nkeys = 1;
+        for (int d = 0; d < 3; d++) { bg.nbin[d] = (bs[d] + G - 1) / G; bg.nkeys *= bg.nbin[d]; }
+        if (bg.nkeys > NFFTB_BIN_MAXKEYS) return false;
+        const int PX = bs[0] + L, PY = bs[1] + L, PZ = bs[2] + L;
+        int best = 1 << 30, bdeg = 1 << 30;
+        bg.PXp = PX; bg.PL = PX * PY;
+        for (int px = PX; px < PX + 16; px++)
+            for (int pl = px * PY; pl < px * PY + 32; pl++) {
+                const int deg = bin_conflict_degree(W, (int)sizeof(C), px, pl);
+                const int size = pl * PZ;
+                if (deg < bdeg || (deg == bdeg && size < best)) { bdeg = deg; best = size; bg.PXp = px; bg.PL = pl; }
+            }
+        bg.PNs = (bg.PL * PZ + 1) & ~1;
+        return true;
+    }
+    static size_t bytes(const BinGeom& bg)
+    {
+        const size_t CH = BinChunk<T>::value;
+        size_t b = sizeof(C) * (size_t)bg.PNs;                               // padded tile
+        b += sizeof(T) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW;             // weight records (sort counters alias them)
+        b += sizeof(C) * CH + sizeof(T) * 3 * CH;                            // staged values and coordinates
+        b += 2 * CH + CH + CH;                                               // order (u16), key (u8), rank (u8)
+        b += 2 * (NFFTB_BIN_MAXKEYS + 8);                                    // bin_start (u16)
+        return b + 16;
+    }
+};
+
+// W consecutive weights of a record (16-byte aligned) -> registers, with the widest loads the width allows
+template <typename T, int W> __device__ __forceinline__ void bin_load_row(const T* __restrict__ p, T (&w)[W])
+{
+    if constexpr (sizeof(T) == 4 && W % 4 == 0) {
+        NFFTB_EMU_ALIGNED(p, 16);
+#pragma unroll
+        for (int k = 0; k < W / 4; k++) {
+            const float4 v = reinterpret_cast<const float4*>(p)[k];
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+    } else if constexpr (W % 2 == 0) {
+        using V2 = typename Cplx<T>::type;
+        NFFTB_EMU_ALIGNED(p, sizeof(V2));
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) {
+            const V2 v = reinterpret_cast<const V2*>(p)[k];
+            w[2 * k] = v.x; w[2 * k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; i++) w[i] = p[i];
+    }
+}
+
+template <typename T, int MT, int W>
+__global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, (sizeof(T) == 4 && W <= 8) ? 2 : 1)
+k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>::type* __restrict__ scratch,
+               const T* __restrict__ xs, const int32_t* __restrict__ perm, const int32_t* __restrict__ items,
+               int item_lo, long long M, GeomDev geo, WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp,
+               BinGeom bg)
+{
+    using C = typename Cplx<T>::type;
+    using BL = BinLayout<T, MT, W>;
+    constexpr int L = BL::L, G = BL::G, RW = BL::RW, NP = BL::NP, ROWS = BL::ROWS;
+    constexpr int NWARP = NFFTB_BIN_WARPS, NTHR = NWARP * 32, CH = BinChunk<T>::value, RND = NFFTB_BIN_ROUND;
+    constexpr int CW = CH / NWARP;                          // nodes ranked by one warp in the counting sort
+    static_assert(CH % NWARP == 0 && CW <= 255, "rank must fit a byte");
+    static_assert(3 * RND <= 32, "one lane per (node, dimension)");
+    static_assert(sizeof(unsigned short) * NWARP * NFFTB_BIN_MAXKEYS <= sizeof(T) * NWARP * RND * RW, "counters alias the records");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* P = reinterpret_cast<C*>(smem_raw);                                          // [PZ][PL] padded tile
+    T* rec = reinterpret_cast<T*>(P + bg.PNs);                                      // [NWARP][RND][RW]
+    unsigned short* cntw = reinterpret_cast<unsigned short*>(rec);                  // [NWARP][nkeys]  (sort only)
+    C* s_v = reinterpret_cast<C*>(rec + NWARP * RND * RW);                          // [CH]
+    T* s_x = reinterpret_cast<T*>(s_v + CH);                                        // [CH][3]
+    unsigned short* order = reinterpret_cast<unsigned short*>(s_x + 3 * CH);        // [CH] bin-sorted chunk-local ids
+    unsigned short* bin_start = order + CH;                                         // [nkeys + 1]
+    unsigned char* key = reinterpret_cast<unsigned char*>(bin_start + NFFTB_BIN_MAXKEYS + 8);   // [CH]
+    unsigned char* rnk = key + CH;                                                  // [CH]
+
+    const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
+    const int tile_id = item[0];
+    const int n_lo = item[1], n_hi = item[2];
+    const int tx = tile_id % geo.nb[0];
+    const int ty = (tile_id / geo.nb[0]) % geo.nb[1];
+    const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
+    const int cx0 = tx * geo.bs[0], cy0 = ty * geo.bs[1], cz0 = tz * geo.bs[2];     // first core cell
+    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
+    const int PXp = bg.PXp, PL = bg.PL, nkeys = bg.nkeys;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    fhat += (long long)blockIdx.y * M;
+    scratch += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)PX * PY * PZ);
+    T* myrec = rec + warp * RND * RW;
+    NFFTB_EMU_ALIGNED(P, 16); NFFTB_EMU_ALIGNED(rec, 16); NFFTB_EMU_ALIGNED(s_v, sizeof(C)); NFFTB_EMU_ALIGNED(s_x, sizeof(T));
+    NFFTB_EMU_ALIGNED(order, 2); NFFTB_EMU_ALIGNED(scratch, 16);
+
+    // per-lane constant row geometry: row r = lane + 32 * p of the W x W window
+    int rowy[NP], rowz[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) { const int r = lane + 32 * p; rowy[p] = r % W; rowz[p] = r / W; }
+    // lane = (node, dimension) of the weight rounds
+    const int wn = lane / 3, wd = lane - 3 * wn;
+    const int wNt = wd == 0 ? geo.Nt[0] : (wd == 1 ? geo.Nt[1] : geo.Nt[2]);
+    const int wc0 = wd == 0 ? cx0 : (wd == 1 ? cy0 : cz0);
+
+    for (int cbase = n_lo; cbase < n_hi; cbase += CH) {
+        const int nc = min(CH, n_hi - cbase);
+        // ---- stage the chunk: global loads first, the tile is zeroed while they are in flight (first chunk)
+        constexpr int NPT = (CH + NTHR - 1) / NTHR;
+        T rx[NPT][3];
+        C rv[NPT];
+#pragma unroll
+        for (int k = 0; k < NPT; k++) {
+            const int q = threadIdx.x + k * NTHR;
+            if (q < nc) {
+                const long long i = (long long)cbase + q;
+                rx[k][0] = xs[i * 3 + 0]; rx[k][1] = xs[i * 3 + 1]; rx[k][2] = xs[i * 3 + 2];
+                rv[k] = fhat[perm[i]];
+            }
+        }
+        if (cbase == n_lo) {
+            uint4* z = reinterpret_cast<uint4*>(P);
+            const int n16 = (int)((sizeof(C) * (size_t)bg.PNs) / 16);
+            for (int q = threadIdx.x; q < n16; q += NTHR) z[q] = make_uint4(0, 0, 0, 0);
+        }
+        for (int q = threadIdx.x; q < NWARP * nkeys; q += NTHR) cntw[q] = 0;
+#pragma unroll
+        for (int k = 0; k < NPT; k++) {
+            const int q = threadIdx.x + k * NTHR;
+            if (q < nc) {
+                T ks;
+                const int b0 = (node_cell<T>(rx[k][0], geo.Nt[0], ks) - cx0) / G;
+                const int b1 = (node_cell<T>(rx[k][1], geo.Nt[1], ks) - cy0) / G;
+                const int b2 = (node_cell<T>(rx[k][2], geo.Nt[2], ks) - cz0) / G;
+                key[q] = (unsigned char)((b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0);
+                s_x[q * 3 + 0] = rx[k][0]; s_x[q * 3 + 1] = rx[k][1]; s_x[q * 3 + 2] = rx[k][2];
+                s_v[q] = rv[k];
+            }
+        }
+        __syncthreads();
+        // ---- stable counting sort of the chunk by bin.  (1) every warp ranks its own contiguous range of the chunk
+        {
+            const int q_end = min(nc, (warp + 1) * CW);
+            unsigned short* mycnt = cntw + warp * nkeys;
+            for (int b0 = warp * CW; b0 < q_end; b0 += 32) {
+                const int q = b0 + lane;
+                const bool on = q < q_end;
+                const unsigned kk = on ? (unsigned)key[q] : 0xffffu;
+                const unsigned peers = __match_any_sync(0xffffffffu, kk);
+                const int r = __popc(peers & lt);
+                int base = 0;
+                if (on) base = mycnt[kk];
+                __syncwarp();
+                if (on) {
+                    rnk[q] = (unsigned char)(base + r);
+                    if (r == 0) mycnt[kk] = (unsigned short)(base + __popc(peers));
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        //      (2) per bin: exclusive offsets of the warps' ranges, and the bin's node count
+        if (threadIdx.x < nkeys) {
+            int run = 0;
+            for (int w = 0; w < NWARP; w++) {
+                const int c = cntw[w * nkeys + threadIdx.x];
+                cntw[w * nkeys + threadIdx.x] = (unsigned short)run;
+                run += c;
+            }
+            bin_start[threadIdx.x] = (unsigned short)run;
+        }
+        __syncthreads();
+        //      (3) exclusive scan of the bin counts by warp 0 (NFFTB_BIN_MAXKEYS / 32 bins per lane)
+        if (warp == 0) {
+            constexpr int KPL = NFFTB_BIN_MAXKEYS / 32;
+            int c[KPL], sum = 0;
+#pragma unroll
+            for (int k = 0; k < KPL; k++) {
+                const int idx = lane * KPL + k;
+                c[k] = idx < nkeys ? (int)bin_start[idx] : 0;
+                sum += c[k];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < KPL; k++) {
+                const int idx = lane * KPL + k;
+                if (idx < nkeys) bin_start[idx] = (unsigned short)run;
+                run += c[k];
+            }
+            if (lane == 31) bin_start[nkeys] = (unsigned short)incl;          // total = nc
+        }
+        __syncthreads();
+        //      (4) scatter
+        for (int q = threadIdx.x; q < nc; q += NTHR) {
+            const int kk = key[q];
+            order[bin_start[kk] + cntw[(q / CW) * nkeys + kk] + rnk[q]] = (unsigned short)q;
+        }
+        __syncthreads();
+
+        // ---- accumulate: S^3 colours, the bins of one colour have disjoint windows and run on different warps
+        const int S = bg.S;
+        for (int ph = 0; ph < S * S * S; ph++) {
+            const int p0 = ph % S, p1 = (ph / S) % S, p2 = ph / (S * S);
+            const int a0n = p0 < bg.nbin[0] ? (bg.nbin[0] - p0 + S - 1) / S : 0;
+            const int a1n = p1 < bg.nbin[1] ? (bg.nbin[1] - p1 + S - 1) / S : 0;
+            const int a2n = p2 < bg.nbin[2] ? (bg.nbin[2] - p2 + S - 1) / S : 0;
+            const int nslots = a0n * a1n * a2n;
+            for (int slot = warp; slot < nslots; slot += NWARP) {
+                const int a0 = slot % a0n, a1 = (slot / a0n) % a1n, a2 = slot / (a0n * a1n);
+                const int b0 = p0 + S * a0, b1 = p1 + S * a1, b2 = p2 + S * a2;
+                const int kk = (b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0;
+                const int lo = bin_start[kk], hi = bin_start[kk + 1];
+                if (hi <= lo) continue;                                   // warp-uniform
+                // window origin in padded-tile coordinates: first tap of the bin's first position (cell b*G -> 1 + b*G)
+                const int o0 = 1 + G * b0, o1 = 1 + G * b1, o2 = 1 + G * b2;
+                const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
+                T ar[NP][W], ai[NP][W];
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+#pragma unroll
+                    for (int i = 0; i < W; i++) { ar[p][i] = (T)0; ai[p][i] = (T)0; }
+                for (int r0 = lo; r0 < hi; r0 += RND) {
+                    const int nn = min(RND, hi - r0);
+                    for (int i = lane; i < RND * RW; i += 32) myrec[i] = (T)0;
+                    __syncwarp();
+                    if (wn < nn) {                                        // weights of (node wn, dimension wd)
+                        const int q = order[r0 + wn];
+                        T ks;
+                        const int c = node_cell<T>(s_x[q * 3 + wd], wNt, ks);
+                        T w[L];
+                        eval_taps<T, MT>(win, pp, ks, c, w);
+                        const int dl = c - wc0 + 1 - wo;                  // first tap inside the window, in [0, G)
+                        T* rn = myrec + wn * RW;
+                        if (wd < 2) {
+#pragma unroll
+                            for (int l = 0; l < L; l++) rn[wd * W + dl + l] = w[l];
+                        } else {
+                            const C v = s_v[q];
+#pragma unroll
+                            for (int l = 0; l < L; l++) { rn[2 * W + 2 * (dl + l)] = w[l] * v.x; rn[2 * W + 2 * (dl + l) + 1] = w[l] * v.y; }
+                        }
+                    }
+                    __syncwarp();
+                    for (int n = 0; n < nn; n++) {
+                        const T* rn = myrec + n * RW;
+                        T wx[W];
+                        bin_load_row<T, W>(rn, wx);
+#pragma unroll
+                        for (int p = 0; p < NP; p++) {
+                            if (NP * 32 == ROWS || lane + 32 * p < ROWS) {
+                                const T wy = rn[W + rowy[p]];
+                                NFFTB_EMU_ALIGNED(rn + 2 * W, sizeof(C));
+                                const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz[p]];
+                                const T fr = wy * vz.x, fi = wy * vz.y;
+#pragma unroll
+                                for (int i = 0; i < W; i++) { ar[p][i] = tfma(wx[i], fr, ar[p][i]); ai[p][i] = tfma(wx[i], fi, ai[p][i]); }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                // one read-modify-write of the window (cells beyond the padded tile carry zero weights only)
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const int Y = o1 + rowy[p], Z = o2 + rowz[p];
+                    if ((NP * 32 == ROWS || lane + 32 * p < ROWS) && Y < PY && Z < PZ) {
+                        C* row = P + (Z * PL + Y * PXp + o0);
+#pragma unroll
+                        for (int i = 0; i < W; i++)
+                            if (o0 + i < PX) { C c = row[i]; c.x += ar[p][i]; c.y += ai[p][i]; row[i] = c; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (n_hi <= n_lo) {                                                   // empty item: the tile is all zeros
+        uint4* z = reinterpret_cast<uint4*>(P);
+        const int n16 = (int)((sizeof(C) * (size_t)bg.PNs) / 16);
+        for (int q = threadIdx.x; q < n16; q += NTHR) z[q] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+    }
+
+    // ---- flush the padded tile to its scratch slot, dense [PZ][PY][PX] (what the gather pass reads)
+    if ((PX & 1) == 0) {
+        const int hx = PX >> 1;
+        const unsigned inv_hx = fastdiv_inv(hx), inv_py = fastdiv_inv(PY);
+        for (int idx = threadIdx.x; idx < PZ * PY * hx; idx += NTHR) {
+            const int row = (int)fastdiv(idx, inv_hx), u = idx - row * hx;
+            const int z = (int)fastdiv(row, inv_py), y = row - z * PY;
+            const C* src = P + (z * PL + y * PXp + 2 * u);
+            const C a = src[0], b = src[1];
+            C* dst = scratch + ((size_t)row * PX + 2 * u);
+            NFFTB_EMU_ALIGNED(dst, 16);
+            if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+            else { dst[0] = a; dst[1] = b; }
+        }
+    } else {
+        const unsigned inv_px = fastdiv_inv(PX), inv_py = fastdiv_inv(PY);
+        for (int idx = threadIdx.x; idx < PZ * PY * PX; idx += NTHR) {
+            const int row = (int)fastdiv(idx, inv_px), x = idx - row * PX;
+            const int z = (int)fastdiv(row, inv_py), y = row - z * PY;
+            scratch[idx] = P[z * PL + y * PXp + x];
+        }
+    }
+}
