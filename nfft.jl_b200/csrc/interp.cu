@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "window.cuh"
 #include "tile3d.cuh"
+#include "interp_bin.cuh"
 
 namespace {
 
@@ -401,6 +402,29 @@ int launch_tile3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, 
     return NFFTB200_OK;
 }
 
+// kernel_mode 7: register-window interpolator (interp_bin.cuh); -1 when it does not apply
+template <typename T, int MT, int W>
+int launch_bin3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi)
+{
+    using C = typename Cplx<T>::type;
+    using IL = InterpBinLayout<T, MT, W>;
+    GeomDev geo = make_geom<T>(p);
+    BinGeom bg;
+    if (!IL::make(geo.bs, bg)) return -1;
+    const size_t smem = IL::bytes(bg);
+    if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64) return -1;
+    auto kern = k_interp_bin3d<T, MT, W>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
+    if (item_hi == item_lo) return NFFTB200_OK;
+    kern<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm,
+                                                                               p->d_items, item_lo, p->M, geo, make_win<T>(p),
+                                                                               make_poly_param<T, MT>(p), bg);
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
 template <typename T>
 int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_complex, int t_lo, int t_hi,
                 long long i_lo, long long i_hi)
@@ -417,6 +441,16 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
     }
     if (nfftb_tiled_ok(p) && is_complex && p->D == 2) {
         const int r = nfftb_interp_2d(p, g, fhat, B, t_lo, t_hi);
+        if (r >= 0) return r;
+    }
+    if (nfftb_tiled_ok(p) && is_complex && p->D == 3 && p->kernel_mode == 7) {
+        int r = -1;                                    // opt-in register-window interpolator (interp_bin.cuh)
+        switch (p->m) {
+            case 2: r = launch_bin3d<T, 2, 8>(p, g, fhat, B, t_lo, t_hi); break;
+            case 3: r = launch_bin3d<T, 3, 8>(p, g, fhat, B, t_lo, t_hi); break;
+            case 4: r = launch_bin3d<T, 4, 10>(p, g, fhat, B, t_lo, t_hi); break;
+            default: break;
+        }
         if (r >= 0) return r;
     }
     if (nfftb_tiled_ok(p) && is_complex && p->D == 3) {

@@ -23,51 +23,7 @@
 // The file holds device code only and is also compiled for the HOST by tests/emu (one OS thread per CUDA thread),
 // which checks the kernel's indexing against a direct evaluation without a GPU.
 #pragma once
-#include "common.cuh"
-#include "window.cuh"
-#include "tile3d.cuh"
-
-// alignment checks of the vector accesses: active only in the host emulation build (tests/emu defines it)
-#ifndef NFFTB_EMU_ALIGNED
-#define NFFTB_EMU_ALIGNED(ptr, bytes)
-#endif
-
-#define NFFTB_BIN_MAXKEYS 256
-#define NFFTB_BIN_WARPS 8
-#define NFFTB_BIN_ROUND 8          // nodes whose weights are evaluated together (lane = node * 3 + dim)
-
-template <typename T> struct BinChunk { static constexpr int value = sizeof(T) == 4 ? 640 : 512; };
-
-struct BinGeom {
-    int G;             // first-tap positions per bin and dimension
-    int S;             // colour stride in bins: windows of bins i and i + S are disjoint
-    int nbin[3];       // bins per dimension = ceil(bs / G)
-    int nkeys;         // nbin[0] * nbin[1] * nbin[2]  (<= NFFTB_BIN_MAXKEYS)
-    int PXp, PL;       // row pitch / plane pitch of the padded tile in shared memory (cells), bank-conflict free
-    int PNs;           // cells of the shared-memory tile (PL * PZ, even)
-};
-
-// bank-conflict degree of the read-modify-write of one pass: lane r touches cell (z*PL + y*PXp + i), i uniform
-inline int bin_conflict_degree(int W, int cell_bytes, int PXp, int PL)
-{
-    const int group = 128 / cell_bytes;                   // lanes served by one wavefront (16 for 8 B, 8 for 16 B)
-    const int wpc = cell_bytes / 4;                       // banks per cell
-    int worst = 1;
-    const int rows = W * W, passes = (rows + 31) / 32;
-    for (int p = 0; p < passes; p++)
-        for (int g0 = 0; g0 < 32; g0 += group) {
-            int cnt[32] = {0};
-            for (int l = g0; l < g0 + group; l++) {
-                const int r = l + 32 * p;
-                if (r >= rows) continue;
-                const long long cell = (long long)(r / W) * PL + (long long)(r % W) * PXp;
-                const int bank = (int)((cell * wpc) % 32);
-                cnt[bank]++;
-            }
-            for (int b = 0; b < 32; b++) worst = cnt[b] > worst ? cnt[b] : worst;
-        }
-    return worst;
-}
+#include "bin_common.cuh"
 
 template <typename T, int MT, int W> struct BinLayout {
     using C = typename Cplx<T>::type;
@@ -77,26 +33,7 @@ template <typename T, int MT, int W> struct BinLayout {
     static constexpr int ROWS = W * W, NP = (ROWS + 31) / 32;
     static_assert(G >= 1, "window narrower than the footprint");
 
-    // returns false if the tile cannot be binned (too many bins)
-    static bool make(const int* bs, BinGeom& bg)
-    {
-        bg.G = G;
-        bg.S = (W + G - 1) / G;
-        bg.nkeys = 1;
-        for (int d = 0; d < 3; d++) { bg.nbin[d] = (bs[d] + G - 1) / G; bg.nkeys *= bg.nbin[d]; }
-        if (bg.nkeys > NFFTB_BIN_MAXKEYS) return false;
-        const int PX = bs[0] + L, PY = bs[1] + L, PZ = bs[2] + L;
-        int best = 1 << 30, bdeg = 1 << 30;
-        bg.PXp = PX; bg.PL = PX * PY;
-        for (int px = PX; px < PX + 16; px++)
-            for (int pl = px * PY; pl < px * PY + 32; pl++) {
-                const int deg = bin_conflict_degree(W, (int)sizeof(C), px, pl);
-                const int size = pl * PZ;
-                if (deg < bdeg || (deg == bdeg && size < best)) { bdeg = deg; best = size; bg.PXp = px; bg.PL = pl; }
-            }
-        bg.PNs = (bg.PL * PZ + 1) & ~1;
-        return true;
-    }
+    static bool make(const int* bs, BinGeom& bg) { return bin_make_geom<T, MT, W>(bs, bg); }
     static size_t bytes(const BinGeom& bg)
     {
         const size_t CH = BinChunk<T>::value;
@@ -109,30 +46,6 @@ template <typename T, int MT, int W> struct BinLayout {
     }
 };
 
-// W consecutive weights of a record (16-byte aligned) -> registers, with the widest loads the width allows
-template <typename T, int W> __device__ __forceinline__ void bin_load_row(const T* __restrict__ p, T (&w)[W])
-{
-    if constexpr (sizeof(T) == 4 && W % 4 == 0) {
-        NFFTB_EMU_ALIGNED(p, 16);
-#pragma unroll
-        for (int k = 0; k < W / 4; k++) {
-            const float4 v = reinterpret_cast<const float4*>(p)[k];
-            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-        }
-    } else if constexpr (W % 2 == 0) {
-        using V2 = typename Cplx<T>::type;
-        NFFTB_EMU_ALIGNED(p, sizeof(V2));
-#pragma unroll
-        for (int k = 0; k < W / 2; k++) {
-            const V2 v = reinterpret_cast<const V2*>(p)[k];
-            w[2 * k] = v.x; w[2 * k + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < W; i++) w[i] = p[i];
-    }
-}
-
 template <typename T, int MT, int W>
 __global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, (sizeof(T) == 4 && W <= 8) ? 2 : 1)
 k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>::type* __restrict__ scratch,
@@ -144,8 +57,6 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     using BL = BinLayout<T, MT, W>;
     constexpr int L = BL::L, G = BL::G, RW = BL::RW, NP = BL::NP, ROWS = BL::ROWS;
     constexpr int NWARP = NFFTB_BIN_WARPS, NTHR = NWARP * 32, CH = BinChunk<T>::value, RND = NFFTB_BIN_ROUND;
-    constexpr int CW = CH / NWARP;                          // nodes ranked by one warp in the counting sort
-    static_assert(CH % NWARP == 0 && CW <= 255, "rank must fit a byte");
     static_assert(3 * RND <= 32, "one lane per (node, dimension)");
     static_assert(sizeof(unsigned short) * NWARP * NFFTB_BIN_MAXKEYS <= sizeof(T) * NWARP * RND * RW, "counters alias the records");
 
@@ -170,7 +81,6 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
     const int PXp = bg.PXp, PL = bg.PL, nkeys = bg.nkeys;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
     fhat += (long long)blockIdx.y * M;
     scratch += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)PX * PY * PZ);
     T* myrec = rec + warp * RND * RW;
@@ -221,70 +131,7 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
             }
         }
         __syncthreads();
-        // ---- stable counting sort of the chunk by bin.  (1) every warp ranks its own contiguous range of the chunk
-        {
-            const int q_end = min(nc, (warp + 1) * CW);
-            unsigned short* mycnt = cntw + warp * nkeys;
-            for (int b0 = warp * CW; b0 < q_end; b0 += 32) {
-                const int q = b0 + lane;
-                const bool on = q < q_end;
-                const unsigned kk = on ? (unsigned)key[q] : 0xffffu;
-                const unsigned peers = __match_any_sync(0xffffffffu, kk);
-                const int r = __popc(peers & lt);
-                int base = 0;
-                if (on) base = mycnt[kk];
-                __syncwarp();
-                if (on) {
-                    rnk[q] = (unsigned char)(base + r);
-                    if (r == 0) mycnt[kk] = (unsigned short)(base + __popc(peers));
-                }
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        //      (2) per bin: exclusive offsets of the warps' ranges, and the bin's node count
-        if (threadIdx.x < nkeys) {
-            int run = 0;
-            for (int w = 0; w < NWARP; w++) {
-                const int c = cntw[w * nkeys + threadIdx.x];
-                cntw[w * nkeys + threadIdx.x] = (unsigned short)run;
-                run += c;
-            }
-            bin_start[threadIdx.x] = (unsigned short)run;
-        }
-        __syncthreads();
-        //      (3) exclusive scan of the bin counts by warp 0 (NFFTB_BIN_MAXKEYS / 32 bins per lane)
-        if (warp == 0) {
-            constexpr int KPL = NFFTB_BIN_MAXKEYS / 32;
-            int c[KPL], sum = 0;
-#pragma unroll
-            for (int k = 0; k < KPL; k++) {
-                const int idx = lane * KPL + k;
-                c[k] = idx < nkeys ? (int)bin_start[idx] : 0;
-                sum += c[k];
-            }
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            int run = incl - sum;
-#pragma unroll
-            for (int k = 0; k < KPL; k++) {
-                const int idx = lane * KPL + k;
-                if (idx < nkeys) bin_start[idx] = (unsigned short)run;
-                run += c[k];
-            }
-            if (lane == 31) bin_start[nkeys] = (unsigned short)incl;          // total = nc
-        }
-        __syncthreads();
-        //      (4) scatter
-        for (int q = threadIdx.x; q < nc; q += NTHR) {
-            const int kk = key[q];
-            order[bin_start[kk] + cntw[(q / CW) * nkeys + kk] + rnk[q]] = (unsigned short)q;
-        }
-        __syncthreads();
+        bin_sort_chunk<CH, NWARP>(nc, nkeys, key, rnk, cntw, bin_start, order);
 
         // ---- accumulate: S^3 colours, the bins of one colour have disjoint windows and run on different warps
         const int S = bg.S;
@@ -310,7 +157,7 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                     for (int i = 0; i < W; i++) { ar[p][i] = (T)0; ai[p][i] = (T)0; }
                 for (int r0 = lo; r0 < hi; r0 += RND) {
                     const int nn = min(RND, hi - r0);
-                    for (int i = lane; i < RND * RW; i += 32) myrec[i] = (T)0;
+                    bin_zero_warp<T>(myrec, RND * RW, lane);
                     __syncwarp();
                     if (wn < nn) {                                        // weights of (node wn, dimension wd)
                         const int q = order[r0 + wn];

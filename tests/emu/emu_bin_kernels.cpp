@@ -1,6 +1,7 @@
-// emu_spread_bin.cpp -- TEST INFRASTRUCTURE: runs k_spread_bin3d (nfft.jl_b200/csrc/spread_bin.cuh, the opt-in
-// register-footprint spreader) on the host through simt_emu.h and compares every padded tile it writes with a direct
-// evaluation (same window weights, double accumulation).  Covers: several bins per warp and colour, bins with more
+// emu_bin_kernels.cpp -- TEST INFRASTRUCTURE: runs the opt-in kernel_mode-7 kernels on the host through simt_emu.h:
+// k_spread_bin3d (nfft.jl_b200/csrc/spread_bin.cuh), whose every padded tile is compared with a direct evaluation
+// (same window weights, double accumulation), and k_interp_bin3d (csrc/interp_bin.cuh), whose every fHat[j] is
+// compared with the direct sum over the periodically wrapped grid.  Covers: several bins per warp and colour, bins with more
 // nodes than one weight round, tiles with more nodes than one staged chunk, split work items, an empty work item,
 // partial last tiles, thin tiles, ntransforms > 1, Float32 and Float64, m = 2, 3, 4.  Each case runs twice and the two
 // results must be bit-identical (the summation order may not depend on thread scheduling).
@@ -12,6 +13,7 @@
 #include "simt_emu.h"
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 #include "../../nfft.jl_b200/csrc/spread_bin.cuh"
+#include "../../nfft.jl_b200/csrc/interp_bin.cuh"
 
 template <typename T, int MT, int W>
 static int run_case(const char* name, const int Nt[3], const int bs[3], int M, int cluster, int B, unsigned seed)
@@ -130,10 +132,54 @@ static int run_case(const char* name, const int Nt[3], const int bs[3], int M, i
                 scale = std::max(scale, std::max(std::fabs(er[q]), std::fabs(ei[q])));
             }
         }
+    // ---- forward interpolation from a random grid (B grids), same nodes / items / weights
+    double iworst = 0, iscale = 0;
+    bool ideterm = true;
+    {
+        using IL = InterpBinLayout<T, MT, W>;
+        BinGeom ig;
+        IL::make(geo.bs, ig);
+        if (IL::bytes(ig) > 227 * 1024) { printf("%s: interp layout too large\n", name); return 1; }
+        std::vector<C> grid((size_t)B * geo.gsz);
+        for (auto& v : grid) { v.x = (T)(U(rng) - 0.5); v.y = (T)(U(rng) - 0.5); }
+        std::vector<C> fo[2];
+        for (int rep = 0; rep < 2; rep++) {
+            fo[rep].assign((size_t)B * M, C{(T)777, (T)777});
+            C* dst = fo[rep].data();
+            emu::launch(emu::Dim3{(unsigned)nitems, (unsigned)B, 1}, NFFTB_BIN_WARPS * 32, [&] {
+                k_interp_bin3d<T, MT, W>(grid.data(), dst, xs.data(), perm.data(), items.data(), 0, (long long)M, geo, win, pp, ig);
+            });
+        }
+        ideterm = std::memcmp(fo[0].data(), fo[1].data(), sizeof(C) * fo[0].size()) == 0;
+        for (int b = 0; b < B; b++)
+            for (int i = 0; i < M; i++) {
+                T w[3][L];
+                int s[3];
+                for (int d = 0; d < 3; d++) {
+                    T ks;
+                    const int c = node_cell<T>(xs[(size_t)3 * i + d], Nt[d], ks);
+                    eval_taps<T, MT>(win, pp, ks, c, w[d]);
+                    s[d] = c - MT + 1;
+                }
+                double ar = 0, ai = 0;
+                for (int l2 = 0; l2 < L; l2++)
+                    for (int l1 = 0; l1 < L; l1++)
+                        for (int l0 = 0; l0 < L; l0++) {
+                            const int gx = ((s[0] + l0) % Nt[0] + Nt[0]) % Nt[0], gy = ((s[1] + l1) % Nt[1] + Nt[1]) % Nt[1],
+                                      gz = ((s[2] + l2) % Nt[2] + Nt[2]) % Nt[2];
+                            const C gv = grid[(size_t)b * geo.gsz + ((size_t)gz * Nt[1] + gy) * Nt[0] + gx];
+                            const double ww = (double)w[0][l0] * (double)w[1][l1] * (double)w[2][l2];
+                            ar += ww * gv.x; ai += ww * gv.y;
+                        }
+                const C got = fo[0][(size_t)b * M + perm[i]];
+                iworst = std::max(iworst, std::max(std::fabs(got.x - ar), std::fabs(got.y - ai)));
+                iscale = std::max(iscale, std::max(std::fabs(ar), std::fabs(ai)));
+            }
+    }
     const double tol = sizeof(T) == 4 ? 2e-5 : 1e-12;
-    const bool ok = worst <= tol * scale && scale > 0;
-    printf("%s: %s  items %d  max|err|/max|ref| %.3e  smem %zu B  pitch (%d,%d)  conflict degree %d  bins %dx%dx%d  colours %d\n",
-           name, ok ? "OK" : "FAIL", nitems, worst / scale, smem, bg.PXp, bg.PL, deg_conf, bg.nbin[0], bg.nbin[1], bg.nbin[2],
+    const bool ok = worst <= tol * scale && scale > 0 && iworst <= tol * iscale && iscale > 0 && ideterm;
+    printf("%s: %s  items %d  spread max|err|/max|ref| %.3e  interp %.3e%s  smem %zu B  pitch (%d,%d)  conflict degree %d  bins %dx%dx%d  colours %d\n",
+           name, ok ? "OK" : "FAIL", nitems, worst / scale, iworst / iscale, ideterm ? "" : " (NOT reproducible)", smem, bg.PXp, bg.PL, deg_conf, bg.nbin[0], bg.nbin[1], bg.nbin[2],
            bg.S * bg.S * bg.S);
     return ok ? 0 : 1;
 }

@@ -4,7 +4,7 @@
 //
 // Include AFTER <cuda_runtime.h> (vector types) and BEFORE the kernel header.  Provides: threadIdx/blockIdx/
 // blockDim/gridDim (thread-local), __syncthreads/__syncwarp, the warp collectives the kernels use
-// (__match_any_sync, __ballot_sync, __shfl_up_sync), the rounding intrinsics and a launch helper.
+// (__match_any_sync, __ballot_sync, __shfl_up_sync, __shfl_xor_sync), the rounding intrinsics and a launch helper.
 #pragma once
 #include <pthread.h>
 
@@ -21,6 +21,7 @@
 #endif
 
 #define __launch_bounds__(...)
+#define NFFTB_EMU 1
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))
 #endif
@@ -92,6 +93,22 @@ inline int __shfl_up_sync(unsigned, int v, int delta)
     pthread_barrier_wait(&w.bar);
     const int r = lane >= delta ? (int)(long long)w.vals[lane - delta] : v;
     pthread_barrier_wait(&w.bar);
+    return r;
+}
+
+template <typename V> inline V __shfl_xor_sync(unsigned, V v, int lane_mask)
+{
+    static_assert(sizeof(V) <= 8, "shuffle emulation moves at most 8 bytes");
+    auto& w = emu::my_warp();
+    const int lane = emu::my_lane();
+    unsigned long long bits = 0;
+    std::memcpy(&bits, &v, sizeof(V));
+    w.vals[lane] = bits;
+    pthread_barrier_wait(&w.bar);
+    const unsigned long long got = w.vals[lane ^ lane_mask];
+    pthread_barrier_wait(&w.bar);
+    V r;
+    std::memcpy(&r, &got, sizeof(V));
     return r;
 }
 
