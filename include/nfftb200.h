@@ -148,7 +148,11 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
  *   4 = auto, but the full (unpruned) cuFFT plan,
  *   5 = auto, but the per-cell form of the gather pass,
  *   6 = node-sharded plans: NCCL reduce-scatter of full-grid replicas instead of the fused spread + slab gather
- *       over peer memory (the baseline the fused path is measured against). */
+ *       over peer memory (the baseline the fused path is measured against).
+ *   7 = 3-D complex transforms, m <= 4: the opt-in register-footprint kernels (csrc/spread_bin.cuh,
+ *       csrc/interp_bin.cuh) -- the nodes of a tile are counting-sorted into bins inside the CTA and the footprints
+ *       of a bin are summed in registers; falls back to mode 0 where they do not apply.  Experimental: verified by
+ *       host emulation of the kernel sources (tests/emu), hardware run pending. */
 int nfftb200_set_kernel_mode(nfftb200_plan* p, int mode);
 /* number of kernels + library calls this plan has launched so far */
 int nfftb200_get_launch_count(nfftb200_plan* p, int64_t* n);

@@ -415,6 +415,8 @@ int launch_bin3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, i
     if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64) return -1;
     auto kern = k_interp_bin3d<T, MT, W>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need the largest shared-memory carve-out (a hint; the kernel is correct without it)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
     kern<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm,

@@ -724,6 +724,8 @@ int launch_bin3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, i
     if (p->timing) { cudaEventRecord(p->evk[0], st); cudaEventRecord(p->evk[1], st); }
     auto kern = k_spread_bin3d<T, MT, W>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need the largest shared-memory carve-out (a hint; the kernel is correct without it)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, st>>>((const C*)fhat, (C*)p->d_tilebuf, (const T*)p->d_xs, p->d_perm,
                                                                         p->d_items, item_lo, p->M, geo, make_win<T>(p),
                                                                         make_poly_param<T, MT>(p), bg);
