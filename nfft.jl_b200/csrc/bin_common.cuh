@@ -19,9 +19,9 @@
 template <typename T> struct BinChunk { static constexpr int value = sizeof(T) == 4 ? 640 : 512; };
 
 struct BinGeom {
-    int G;             // first-tap positions per bin and dimension
+    int G;             // first-tap positions per bin and dimension (the last bin of a period of W holds fewer)
     int S;             // colour stride in bins: windows of bins i and i + S are disjoint
-    int nbin[3];       // bins per dimension = ceil(bs / G)
+    int nbin[3];       // bins per dimension (bin_of(bs - 1) + 1)
     int nkeys;         // nbin[0] * nbin[1] * nbin[2]  (<= NFFTB_BIN_MAXKEYS)
     int PXp, PL;       // row pitch / plane pitch of the padded tile in shared memory (cells), bank-conflict free
     int PNs;           // cells of the shared-memory tile (PL * PZ, even)
@@ -49,6 +49,22 @@ inline int bin_conflict_degree(int W, int cell_bytes, int PXp, int PL)
     return worst;
 }
 
+// Bin layout along one dimension: first-tap positions are grouped with period W into S = ceil(W/G) bins of G, ..., G and
+// W - (S-1)G positions, so that bins b and b + S start exactly W positions apart (their W-wide windows are disjoint,
+// which is what the colouring needs) and the bins of one colour have the same size in every period (balanced warps).
+template <int W, int G> __host__ __device__ __forceinline__ int bin_of(int lc)
+{
+    constexpr int S = (W + G - 1) / G;
+    const int per = lc / W, r = (lc - per * W) / G;
+    return S * per + (r < S - 1 ? r : S - 1);
+}
+template <int W, int G> __host__ __device__ __forceinline__ int bin_first(int b)
+{
+    constexpr int S = (W + G - 1) / G;
+    const int per = b / S;
+    return W * per + G * (b - per * S);
+}
+
 // bins / pitches for a W-wide window and a 2m-tap footprint; false if the tile has too many bins
 template <typename T, int MT, int W> inline bool bin_make_geom(const int* bs, BinGeom& bg)
 {
@@ -58,7 +74,7 @@ template <typename T, int MT, int W> inline bool bin_make_geom(const int* bs, Bi
     bg.G = G;
     bg.S = (W + G - 1) / G;
     bg.nkeys = 1;
-    for (int d = 0; d < 3; d++) { bg.nbin[d] = (bs[d] + G - 1) / G; bg.nkeys *= bg.nbin[d]; }
+    for (int d = 0; d < 3; d++) { bg.nbin[d] = bin_of<W, G>(bs[d] - 1) + 1; bg.nkeys *= bg.nbin[d]; }
     if (bg.nkeys > NFFTB_BIN_MAXKEYS) return false;
     const int PX = bs[0] + L, PY = bs[1] + L, PZ = bs[2] + L;
     int best = 1 << 30, bdeg = 1 << 30;

@@ -136,9 +136,9 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
             const long long i = (long long)cbase + q;
             const T x0 = xs[i * 3 + 0], x1 = xs[i * 3 + 1], x2 = xs[i * 3 + 2];
             T ks;
-            const int b0 = (node_cell<T>(x0, geo.Nt[0], ks) - cx0) / G;
-            const int b1 = (node_cell<T>(x1, geo.Nt[1], ks) - cy0) / G;
-            const int b2 = (node_cell<T>(x2, geo.Nt[2], ks) - cz0) / G;
+            const int b0 = bin_of<W, G>(node_cell<T>(x0, geo.Nt[0], ks) - cx0);
+            const int b1 = bin_of<W, G>(node_cell<T>(x1, geo.Nt[1], ks) - cy0);
+            const int b2 = bin_of<W, G>(node_cell<T>(x2, geo.Nt[2], ks) - cz0);
             key[q] = (unsigned char)((b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0);
             s_x[q * 3 + 0] = x0; s_x[q * 3 + 1] = x1; s_x[q * 3 + 2] = x2;
             s_j[q] = perm[i];
@@ -151,7 +151,7 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
             const int lo = bin_start[kk], hi = bin_start[kk + 1];
             if (hi <= lo) continue;                                         // warp-uniform
             const int b0 = kk % bg.nbin[0], b1 = (kk / bg.nbin[0]) % bg.nbin[1], b2 = kk / (bg.nbin[0] * bg.nbin[1]);
-            const int o0 = 1 + G * b0, o1 = 1 + G * b1, o2 = 1 + G * b2;    // window origin, padded-tile coordinates
+            const int o0 = 1 + bin_first<W, G>(b0), o1 = 1 + bin_first<W, G>(b1), o2 = 1 + bin_first<W, G>(b2);    // window origin, padded-tile coordinates
             const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
             // the bin's window -> registers (cells beyond the padded tile meet zero weights only)
             T gr[NP][W], gi[NP][W];

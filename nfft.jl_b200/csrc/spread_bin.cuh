@@ -122,9 +122,9 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
             const int q = threadIdx.x + k * NTHR;
             if (q < nc) {
                 T ks;
-                const int b0 = (node_cell<T>(rx[k][0], geo.Nt[0], ks) - cx0) / G;
-                const int b1 = (node_cell<T>(rx[k][1], geo.Nt[1], ks) - cy0) / G;
-                const int b2 = (node_cell<T>(rx[k][2], geo.Nt[2], ks) - cz0) / G;
+                const int b0 = bin_of<W, G>(node_cell<T>(rx[k][0], geo.Nt[0], ks) - cx0);
+                const int b1 = bin_of<W, G>(node_cell<T>(rx[k][1], geo.Nt[1], ks) - cy0);
+                const int b2 = bin_of<W, G>(node_cell<T>(rx[k][2], geo.Nt[2], ks) - cz0);
                 key[q] = (unsigned char)((b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0);
                 s_x[q * 3 + 0] = rx[k][0]; s_x[q * 3 + 1] = rx[k][1]; s_x[q * 3 + 2] = rx[k][2];
                 s_v[q] = rv[k];
@@ -148,7 +148,7 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                 const int lo = bin_start[kk], hi = bin_start[kk + 1];
                 if (hi <= lo) continue;                                   // warp-uniform
                 // window origin in padded-tile coordinates: first tap of the bin's first position (cell b*G -> 1 + b*G)
-                const int o0 = 1 + G * b0, o1 = 1 + G * b1, o2 = 1 + G * b2;
+                const int o0 = 1 + bin_first<W, G>(b0), o1 = 1 + bin_first<W, G>(b1), o2 = 1 + bin_first<W, G>(b2);
                 const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
                 T ar[NP][W], ai[NP][W];
 #pragma unroll
