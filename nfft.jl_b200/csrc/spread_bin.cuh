@@ -6,8 +6,9 @@
 // bound by the 128 B/clk shared-memory pipe.  Here the footprints of SEVERAL nodes are summed in
 // REGISTERS first and shared memory sees one read-modify-write per bin:
 //   * the nodes of the tile (already contiguous after the plan-time sort) are counting-sorted inside the CTA into
-//     bins of G^3 consecutive first-tap positions, G = W - 2m + 1, so that every node of a bin has its (2m)^3 taps
-//     inside one W^3 window (W = 8 for m <= 3);
+//     bins of up to G^3 consecutive first-tap positions, G = W - 2m + 1, so that every node of a bin has its (2m)^3
+//     taps inside one W^3 window (W = 8 for m <= 3; per dimension the positions are cut with period W into bins of
+//     3, 3, 2 for m = 3, see bin_of in bin_common.cuh);
 //   * one warp accumulates one bin: lane r owns the x-row (y, z) = (r % W, r / W) of the window (W complex
 //     accumulators per pass, ceil(W*W/32) passes), the node's weights are laid out on the window (zeros outside
 //     the node's taps) so the inner loop is W*2 FFMA per pass and node with no address arithmetic;
