@@ -147,10 +147,14 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
         bin_sort_chunk<CH, NWARP>(nc, nkeys, key, rnk, cntw, bin_start, order);
         if (cbase == n_lo) { bin_copy_wait(); __syncthreads(); }            // tile resident
 
-        for (int kk = warp; kk < nkeys; kk += NWARP) {
+        int kk = -1;
+        for (int b2 = 0; b2 < bg.nbin[2]; b2++)
+        for (int b1 = 0; b1 < bg.nbin[1]; b1++)
+        for (int b0 = 0; b0 < bg.nbin[0]; b0++) {
+            kk++;                                                           // bin key, dealt to the warps round-robin
+            if ((kk & (NWARP - 1)) != warp) continue;
             const int lo = bin_start[kk], hi = bin_start[kk + 1];
             if (hi <= lo) continue;                                         // warp-uniform
-            const int b0 = kk % bg.nbin[0], b1 = (kk / bg.nbin[0]) % bg.nbin[1], b2 = kk / (bg.nbin[0] * bg.nbin[1]);
             const int o0 = 1 + bin_first<W, G>(b0), o1 = 1 + bin_first<W, G>(b1), o2 = 1 + bin_first<W, G>(b2);    // window origin, padded-tile coordinates
             const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
             // the bin's window -> registers (cells beyond the padded tile meet zero weights only)
@@ -160,17 +164,24 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                 const int Y = o1 + rowy[p], Z = o2 + rowz[p];
                 const bool rowok = (NP * 32 == ROWS || lane + 32 * p < ROWS) && Y < PY && Z < PZ;
                 const C* row = P + (Z * PL + Y * PXp + o0);
+                if (o0 + W <= PX) {                                         // warp-uniform: all but the last bin of a row
 #pragma unroll
-                for (int i = 0; i < W; i++) {
-                    C c = make_c<T>(0, 0);
-                    if (rowok && o0 + i < PX) c = row[i];
-                    gr[p][i] = c.x; gi[p][i] = c.y;
+                    for (int i = 0; i < W; i++) {
+                        C c = make_c<T>(0, 0);
+                        if (rowok) c = row[i];
+                        gr[p][i] = c.x; gi[p][i] = c.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < W; i++) {
+                        C c = make_c<T>(0, 0);
+                        if (rowok && o0 + i < PX) c = row[i];
+                        gr[p][i] = c.x; gi[p][i] = c.y;
+                    }
                 }
             }
             for (int r0 = lo; r0 < hi; r0 += RND) {
                 const int nn = min(RND, hi - r0);
-                bin_zero_warp<T>(myrec, RND * RW, lane);
-                __syncwarp();
                 if (wn < nn) {                                              // weights of (node wn, dimension wd)
                     const int q = order[r0 + wn];
                     T ks;
@@ -178,9 +189,11 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                     T w[L];
                     eval_taps<T, MT>(win, pp, ks, c, w);
                     const int dl = c - wc0 + 1 - wo;                        // first tap inside the window, in [0, G)
-                    T* rn = myrec + wn * RW + wd * W + dl;
+                    T* rn = myrec + wn * RW + wd * W;                       // 2m taps at [dl, dl + 2m), zeros elsewhere
 #pragma unroll
-                    for (int l = 0; l < L; l++) rn[l] = w[l];
+                    for (int l = 0; l < L; l++) rn[dl + l] = w[l];
+#pragma unroll
+                    for (int j = 0; j < W - L; j++) rn[j < dl ? j : j + L] = (T)0;
                 }
                 __syncwarp();
                 T v[2 * RND];

@@ -135,16 +135,15 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
         bin_sort_chunk<CH, NWARP>(nc, nkeys, key, rnk, cntw, bin_start, order);
 
         // ---- accumulate: S^3 colours, the bins of one colour have disjoint windows and run on different warps
-        const int S = bg.S;
+        constexpr int S = (W + G - 1) / G;
         for (int ph = 0; ph < S * S * S; ph++) {
             const int p0 = ph % S, p1 = (ph / S) % S, p2 = ph / (S * S);
-            const int a0n = p0 < bg.nbin[0] ? (bg.nbin[0] - p0 + S - 1) / S : 0;
-            const int a1n = p1 < bg.nbin[1] ? (bg.nbin[1] - p1 + S - 1) / S : 0;
-            const int a2n = p2 < bg.nbin[2] ? (bg.nbin[2] - p2 + S - 1) / S : 0;
-            const int nslots = a0n * a1n * a2n;
-            for (int slot = warp; slot < nslots; slot += NWARP) {
-                const int a0 = slot % a0n, a1 = (slot / a0n) % a1n, a2 = slot / (a0n * a1n);
-                const int b0 = p0 + S * a0, b1 = p1 + S * a1, b2 = p2 + S * a2;
+            // the bins of this colour, dealt to the warps round-robin (a 16^3 tile has 2 x 2 x 2 per colour: one each)
+            int slot = 0;
+            for (int b2 = p2; b2 < bg.nbin[2]; b2 += S)
+            for (int b1 = p1; b1 < bg.nbin[1]; b1 += S)
+            for (int b0 = p0; b0 < bg.nbin[0]; b0 += S) {
+                if (((slot++) & (NWARP - 1)) != warp) continue;
                 const int kk = (b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0;
                 const int lo = bin_start[kk], hi = bin_start[kk + 1];
                 if (hi <= lo) continue;                                   // warp-uniform
@@ -158,8 +157,6 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                     for (int i = 0; i < W; i++) { ar[p][i] = (T)0; ai[p][i] = (T)0; }
                 for (int r0 = lo; r0 < hi; r0 += RND) {
                     const int nn = min(RND, hi - r0);
-                    bin_zero_warp<T>(myrec, RND * RW, lane);
-                    __syncwarp();
                     if (wn < nn) {                                        // weights of (node wn, dimension wd)
                         const int q = order[r0 + wn];
                         T ks;
@@ -168,13 +165,19 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                         eval_taps<T, MT>(win, pp, ks, c, w);
                         const int dl = c - wc0 + 1 - wo;                  // first tap inside the window, in [0, G)
                         T* rn = myrec + wn * RW;
+                        // the 2m taps at window positions [dl, dl + 2m), zeros in the other W - 2m positions
                         if (wd < 2) {
 #pragma unroll
                             for (int l = 0; l < L; l++) rn[wd * W + dl + l] = w[l];
+#pragma unroll
+                            for (int j = 0; j < W - L; j++) rn[wd * W + (j < dl ? j : j + L)] = (T)0;
                         } else {
                             const C v = s_v[q];
+                            C* rz = reinterpret_cast<C*>(rn + 2 * W);
 #pragma unroll
-                            for (int l = 0; l < L; l++) { rn[2 * W + 2 * (dl + l)] = w[l] * v.x; rn[2 * W + 2 * (dl + l) + 1] = w[l] * v.y; }
+                            for (int l = 0; l < L; l++) rz[dl + l] = make_c<T>(w[l] * v.x, w[l] * v.y);
+#pragma unroll
+                            for (int j = 0; j < W - L; j++) rz[j < dl ? j : j + L] = make_c<T>(0, 0);
                         }
                     }
                     __syncwarp();
@@ -202,9 +205,14 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                     const int Y = o1 + rowy[p], Z = o2 + rowz[p];
                     if ((NP * 32 == ROWS || lane + 32 * p < ROWS) && Y < PY && Z < PZ) {
                         C* row = P + (Z * PL + Y * PXp + o0);
+                        if (o0 + W <= PX) {                               // warp-uniform: all but the last bin of a row
 #pragma unroll
-                        for (int i = 0; i < W; i++)
-                            if (o0 + i < PX) { C c = row[i]; c.x += ar[p][i]; c.y += ai[p][i]; row[i] = c; }
+                            for (int i = 0; i < W; i++) { C c = row[i]; c.x += ar[p][i]; c.y += ai[p][i]; row[i] = c; }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < W; i++)
+                                if (o0 + i < PX) { C c = row[i]; c.x += ar[p][i]; c.y += ai[p][i]; row[i] = c; }
+                        }
                     }
                 }
             }
