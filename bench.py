@@ -290,22 +290,24 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh_:
-            traffic = json.load(fh_).get("spread_dram_bytes_per_launch")
+            traffic = json.load(fh_).get("spread_dram_bytes_per_launch" if args.kernel_mode != 7 else "spread_bin_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "adjoint gridding: k_spread_sub3d<float,3> + k_gather_cols3d (convolve_transpose!)",
+    spread_kernel = "k_spread_bin3d<float,3,8>" if args.kernel_mode == 7 else "k_spread_sub3d<float,3>"
+    interp_kernel = "k_interp_bin3d<float,3,8>" if args.kernel_mode == 7 else "k_interp_row3d<float,3>"
+    roofline = {"bound": "hbm", "kernel": f"adjoint gridding: {spread_kernel} + k_gather_cols3d (convolve_transpose!)",
                 "achieved": abytes / t_spread / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": abytes / t_spread / 1e9 / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": abytes, "us_per_launch": t_spread * 1e6,
                 "note": "3-D spreading is shared-memory-bound (216 complex RMWs/node); HBM fraction is the contract metric",
-                "interp": {"kernel": "k_interp_row3d<float,3> (convolve!)", "achieved": abytes / t_interp / 1e9,
+                "interp": {"kernel": f"{interp_kernel} (convolve!)", "achieved": abytes / t_interp / 1e9,
                            "frac": abytes / t_interp / 1e9 / peak, "us_per_launch": t_interp * 1e6}}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "ntransforms": world, "sharding": "batch (one transform per GPU)",
-                   "precompute": "POLYNOMIAL", "blockSize": list(p.params.blockSize),
+                   "precompute": "POLYNOMIAL", "blockSize": list(p.params.blockSize), "kernel_mode": args.kernel_mode,
                    "l2": "flushed between timed iterations (256 MiB write, untimed)",
                    "step": "1 forward + 1 adjoint NFFT; value = n_gpus*2*M/t_step"},
         "forward_pts_per_s": M / sum(phases[n] for n in ("deconv", "fft", "conv")) * args.steps,

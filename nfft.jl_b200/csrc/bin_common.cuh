@@ -71,6 +71,15 @@ template <typename T, int MT, int W> inline bool bin_make_geom(const int* bs, Bi
     using C = typename Cplx<T>::type;
     constexpr int L = 2 * MT, G = W - L + 1;
     static_assert(G >= 1, "window narrower than the footprint");
+    // the pitch search costs ~50 us of host time: remember the last tile size per instantiation and thread
+    thread_local int last_bs[3] = {-1, -1, -1};
+    thread_local BinGeom last_bg;
+    thread_local bool last_ok = false;
+    if (last_bs[0] == bs[0] && last_bs[1] == bs[1] && last_bs[2] == bs[2]) { bg = last_bg; return last_ok; }
+    struct Remember {
+        const int* bs; BinGeom& bg; bool ok = false;
+        ~Remember() { last_bs[0] = bs[0]; last_bs[1] = bs[1]; last_bs[2] = bs[2]; last_bg = bg; last_ok = ok; }
+    } rem{bs, bg};
     bg.G = G;
     bg.S = (W + G - 1) / G;
     bg.nkeys = 1;
@@ -86,6 +95,7 @@ template <typename T, int MT, int W> inline bool bin_make_geom(const int* bs, Bi
             if (deg < bdeg || (deg == bdeg && size < best)) { bdeg = deg; best = size; bg.PXp = px; bg.PL = pl; }
         }
     bg.PNs = (bg.PL * PZ + 1) & ~1;
+    rem.ok = true;
     return true;
 }
 
