@@ -3,7 +3,7 @@
 // (same window weights, double accumulation), and k_interp_bin3d (csrc/interp_bin.cuh), whose every fHat[j] is
 // compared with the direct sum over the periodically wrapped grid.  Covers: several bins per warp and colour, bins with more
 // nodes than one weight round, tiles with more nodes than one staged chunk, split work items, an empty work item,
-// partial last tiles, thin tiles, ntransforms > 1, Float32 and Float64, m = 2, 3, 4.  Each case runs twice and the two
+// partial last tiles, thin tiles, ntransforms > 1, Float32 and Float64, m = 2, 3, 4, the three window evaluation modes.  Each case runs twice and the two
 // results must be bit-identical (the summation order may not depend on thread scheduling).
 #include <cuda_runtime.h>
 
@@ -16,7 +16,8 @@ inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 #include "../../nfft.jl_b200/csrc/interp_bin.cuh"
 
 template <typename T, int MT, int W>
-static int run_case(const char* name, const int Nt[3], const int bs[3], int M, int cluster, int B, unsigned seed)
+static int run_case(const char* name, const int Nt[3], const int bs[3], int M, int cluster, int B, unsigned seed,
+                    int mode = NFFTB200_POLYNOMIAL)
 {
     using C = typename Cplx<T>::type;
     using BL = BinLayout<T, MT, W>;
@@ -83,7 +84,13 @@ static int run_case(const char* name, const int Nt[3], const int bs[3], int M, i
     for (int l = 0; l < L; l++)
         for (int r = 0; r < deg; r++) pp.c[l * deg + r] = (T)((U(rng) - 0.3) / (r + 1));
     WinDev<T> win{};
-    win.m = MT; win.mode = NFFTB200_POLYNOMIAL; win.window = NFFTB200_KAISER_BESSEL;
+    win.m = MT; win.mode = mode; win.window = NFFTB200_KAISER_BESSEL;
+    // LINEAR: a synthetic even lookup table of 2048 intervals (|u| in [0, m] grid units); FULL: exact Kaiser-Bessel
+    const int lut = 2048;
+    std::vector<T> lin(lut + 2);
+    for (int i = 0; i < lut + 2; i++) { const double u = (double)i / lut; lin[i] = (T)(std::exp(-4.0 * u * u) * (1.0 + 0.1 * u)); }
+    win.lin = lin.data(); win.lin_scale = lut / MT;
+    win.b = (T)(3.141592653589793 * (2.0 - 1.0 / 2.0));
 
     const int PX = bs[0] + L, PY = bs[1] + L, PZ = bs[2] + L;
     const size_t PN = (size_t)PX * PY * PZ;
@@ -197,6 +204,8 @@ int main()
     bad += run_case<float, 4, 10>("f32 m=4 (W=10) 32^3", n32, b16, 2000, 100, 1, 5);
     bad += run_case<double, 4, 10>("f64 m=4 (W=10) 32^3", n32, b16, 1200, 0, 1, 6);
     bad += run_case<float, 3, 8>("f32 m=3 thin tiles 16x16x8", nthin, bthin, 1500, 0, 1, 7);
+    bad += run_case<float, 3, 8>("f32 m=3 LINEAR lookup table", n32, b16, 1500, 0, 1, 8, NFFTB200_LINEAR);
+    bad += run_case<double, 3, 8>("f64 m=3 FULL (exact Kaiser-Bessel)", n32, b16, 1500, 0, 1, 9, NFFTB200_FULL);
     printf(bad ? "FAILED\n" : "ALL OK\n");
     return bad ? 1 : 0;
 }
