@@ -184,7 +184,8 @@ static int run_case(const char* name, const int Nt[3], const int bs[3], int M, i
             }
     }
     const double tol = sizeof(T) == 4 ? 2e-5 : 1e-12;
-    const bool ok = worst <= tol * scale && scale > 0 && iworst <= tol * iscale && iscale > 0 && ideterm;
+    // the searched pitches must make the window rows of a pass bank-conflict free
+    const bool ok = worst <= tol * scale && scale > 0 && iworst <= tol * iscale && iscale > 0 && ideterm && deg_conf == 1;
     printf("%s: %s  items %d  spread max|err|/max|ref| %.3e  interp %.3e%s  smem %zu B  pitch (%d,%d)  conflict degree %d  bins %dx%dx%d  colours %d\n",
            name, ok ? "OK" : "FAIL", nitems, worst / scale, iworst / iscale, ideterm ? "" : " (NOT reproducible)", smem, bg.PXp, bg.PL, deg_conf, bg.nbin[0], bg.nbin[1], bg.nbin[2],
            bg.S * bg.S * bg.S);
