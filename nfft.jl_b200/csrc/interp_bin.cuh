@@ -158,7 +158,7 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
             const int o0 = 1 + bin_first<W, G>(b0), o1 = 1 + bin_first<W, G>(b1), o2 = 1 + bin_first<W, G>(b2);    // window origin, padded-tile coordinates
             const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
             // the bin's window -> registers (cells beyond the padded tile meet zero weights only)
-            T gr[NP][W], gi[NP][W];
+            BinRow<T, W> win_row[NP];
 #pragma unroll
             for (int p = 0; p < NP; p++) {
                 const int Y = o1 + rowy[p], Z = o2 + rowz[p];
@@ -169,14 +169,14 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                     for (int i = 0; i < W; i++) {
                         C c = make_c<T>(0, 0);
                         if (rowok) c = row[i];
-                        gr[p][i] = c.x; gi[p][i] = c.y;
+                        win_row[p].set(i, c.x, c.y);
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < W; i++) {
                         C c = make_c<T>(0, 0);
                         if (rowok && o0 + i < PX) c = row[i];
-                        gr[p][i] = c.x; gi[p][i] = c.y;
+                        win_row[p].set(i, c.x, c.y);
                     }
                 }
             }
@@ -210,9 +210,8 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                             if (NP * 32 == ROWS || lane + 32 * p < ROWS) {
                                 const T wyp = (32 % W == 0) ? wy : rn[W + rowy[p]];
                                 const T wyz = wyp * rn[2 * W + rowz[p]];
-                                T a = (T)0, b = (T)0;
-#pragma unroll
-                                for (int i = 0; i < W; i++) { a = tfma(wx[i], gr[p][i], a); b = tfma(wx[i], gi[p][i], b); }
+                                T a, b;
+                                win_row[p].dot(wx, a, b);
                                 sx = tfma(wyz, a, sx); sy = tfma(wyz, b, sy);
                             }
                         }

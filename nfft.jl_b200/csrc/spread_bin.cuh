@@ -150,11 +150,9 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                 // window origin in padded-tile coordinates: first tap of the bin's first position (cell b*G -> 1 + b*G)
                 const int o0 = 1 + bin_first<W, G>(b0), o1 = 1 + bin_first<W, G>(b1), o2 = 1 + bin_first<W, G>(b2);
                 const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
-                T ar[NP][W], ai[NP][W];
+                BinRow<T, W> acc[NP];
 #pragma unroll
-                for (int p = 0; p < NP; p++)
-#pragma unroll
-                    for (int i = 0; i < W; i++) { ar[p][i] = (T)0; ai[p][i] = (T)0; }
+                for (int p = 0; p < NP; p++) acc[p].zero();
                 for (int r0 = lo; r0 < hi; r0 += RND) {
                     const int nn = min(RND, hi - r0);
                     if (wn < nn) {                                        // weights of (node wn, dimension wd)
@@ -191,9 +189,7 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                                 const T wy = rn[W + rowy[p]];
                                 NFFTB_EMU_ALIGNED(rn + 2 * W, sizeof(C));
                                 const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz[p]];
-                                const T fr = wy * vz.x, fi = wy * vz.y;
-#pragma unroll
-                                for (int i = 0; i < W; i++) { ar[p][i] = tfma(wx[i], fr, ar[p][i]); ai[p][i] = tfma(wx[i], fi, ai[p][i]); }
+                                acc[p].axpy(wx, wy * vz.x, wy * vz.y);
                             }
                         }
                     }
@@ -207,11 +203,11 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                         C* row = P + (Z * PL + Y * PXp + o0);
                         if (o0 + W <= PX) {                               // warp-uniform: all but the last bin of a row
 #pragma unroll
-                            for (int i = 0; i < W; i++) { C c = row[i]; c.x += ar[p][i]; c.y += ai[p][i]; row[i] = c; }
+                            for (int i = 0; i < W; i++) { C c = row[i]; c.x += acc[p].re(i); c.y += acc[p].im(i); row[i] = c; }
                         } else {
 #pragma unroll
                             for (int i = 0; i < W; i++)
-                                if (o0 + i < PX) { C c = row[i]; c.x += ar[p][i]; c.y += ai[p][i]; row[i] = c; }
+                                if (o0 + i < PX) { C c = row[i]; c.x += acc[p].re(i); c.y += acc[p].im(i); row[i] = c; }
                         }
                     }
                 }
