@@ -226,72 +226,65 @@ template <typename T, int W> __device__ __forceinline__ void bin_load_row(const 
     }
 }
 
-// One x-row of a bin window in registers: W complex cells, kept as separate real / imaginary vectors.  The Float32
-// specialisation packs neighbouring cells into float2 pairs and uses the packed FP32 FMA of sm_100 (__ffma2_rn,
-// SASS FFMA2: two IEEE fmas per issue slot) -- the register kernels are bound by FMA issue, so this halves their
-// inner loops.  Results are bit-identical to the scalar form (each lane of FFMA2 is a plain fma).
+// One x-row of a bin window in registers: W complex cells.  The Float32 specialisation keeps every cell as a
+// (re, im) float2 -- the layout of the tile in shared memory -- and uses the packed FP32 instructions of sm_100
+// (__ffma2_rn / __fmul2_rn / __fadd2_rn, SASS FFMA2 / FMUL2 / FADD2: two IEEE operations per issue slot, the scalar
+// weight enters as a broadcast operand).  The register kernels are bound by FMA issue, so this halves their inner
+// loops; results are bit-identical to the scalar form (each half of a packed operation is a plain fma / add).
 template <typename T, int W> struct BinRow {
+    using C = typename Cplx<T>::type;
     T r[W], i[W];
     __device__ __forceinline__ void zero()
     {
 #pragma unroll
         for (int k = 0; k < W; k++) { r[k] = (T)0; i[k] = (T)0; }
     }
-    __device__ __forceinline__ void set(int k, T re, T im) { r[k] = re; i[k] = im; }
-    __device__ __forceinline__ T re(int k) const { return r[k]; }
-    __device__ __forceinline__ T im(int k) const { return i[k]; }
-    // row += wx * (fr, fi)
-    __device__ __forceinline__ void axpy(const T (&wx)[W], T fr, T fi)
+    __device__ __forceinline__ void set(int k, C c) { r[k] = c.x; i[k] = c.y; }
+    // cell += row[k]
+    __device__ __forceinline__ void add_to(C& cell, int k) const { cell.x += r[k]; cell.y += i[k]; }
+    // row += wx * (wy * vz)
+    __device__ __forceinline__ void axpy(const T (&wx)[W], T wy, C vz)
     {
+        const T fr = wy * vz.x, fi = wy * vz.y;
 #pragma unroll
         for (int k = 0; k < W; k++) { r[k] = tfma(wx[k], fr, r[k]); i[k] = tfma(wx[k], fi, i[k]); }
     }
-    // (a, b) = sum_k wx[k] * row[k]
-    __device__ __forceinline__ void dot(const T (&wx)[W], T& a, T& b) const
+    // s += wyz * sum_k wx[k] * row[k]
+    __device__ __forceinline__ void dot_acc(const T (&wx)[W], T wyz, C& s) const
     {
-        a = (T)0; b = (T)0;
+        T a = (T)0, b = (T)0;
 #pragma unroll
         for (int k = 0; k < W; k++) { a = tfma(wx[k], r[k], a); b = tfma(wx[k], i[k], b); }
+        s.x = tfma(wyz, a, s.x); s.y = tfma(wyz, b, s.y);
     }
 };
 
 #ifdef NFFTB_EMU
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 #endif
 
 template <int W> struct BinRow<float, W> {
-    static_assert(W % 2 == 0, "cells are paired");
-    float2 r[W / 2], i[W / 2];
+    float2 c[W];
     __device__ __forceinline__ void zero()
     {
 #pragma unroll
-        for (int k = 0; k < W / 2; k++) { r[k] = make_float2(0.f, 0.f); i[k] = make_float2(0.f, 0.f); }
+        for (int k = 0; k < W; k++) c[k] = make_float2(0.f, 0.f);
     }
-    __device__ __forceinline__ void set(int k, float re_, float im_)
+    __device__ __forceinline__ void set(int k, float2 v) { c[k] = v; }
+    __device__ __forceinline__ void add_to(float2& cell, int k) const { cell = __fadd2_rn(cell, c[k]); }
+    __device__ __forceinline__ void axpy(const float (&wx)[W], float wy, float2 vz)
     {
-        if (k & 1) { r[k >> 1].y = re_; i[k >> 1].y = im_; } else { r[k >> 1].x = re_; i[k >> 1].x = im_; }
-    }
-    __device__ __forceinline__ float re(int k) const { return (k & 1) ? r[k >> 1].y : r[k >> 1].x; }
-    __device__ __forceinline__ float im(int k) const { return (k & 1) ? i[k >> 1].y : i[k >> 1].x; }
-    __device__ __forceinline__ void axpy(const float (&wx)[W], float fr, float fi)
-    {
-        const float2 f2r = make_float2(fr, fr), f2i = make_float2(fi, fi);
+        const float2 f = __fmul2_rn(make_float2(wy, wy), vz);
 #pragma unroll
-        for (int k = 0; k < W / 2; k++) {
-            const float2 w2 = make_float2(wx[2 * k], wx[2 * k + 1]);
-            r[k] = __ffma2_rn(w2, f2r, r[k]);
-            i[k] = __ffma2_rn(w2, f2i, i[k]);
-        }
+        for (int k = 0; k < W; k++) c[k] = __ffma2_rn(make_float2(wx[k], wx[k]), f, c[k]);
     }
-    __device__ __forceinline__ void dot(const float (&wx)[W], float& a, float& b) const
+    __device__ __forceinline__ void dot_acc(const float (&wx)[W], float wyz, float2& s) const
     {
-        float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
+        float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < W / 2; k++) {
-            const float2 w2 = make_float2(wx[2 * k], wx[2 * k + 1]);
-            a2 = __ffma2_rn(w2, r[k], a2);
-            b2 = __ffma2_rn(w2, i[k], b2);
-        }
-        a = a2.x + a2.y; b = b2.x + b2.y;
+        for (int k = 0; k < W; k++) a = __ffma2_rn(make_float2(wx[k], wx[k]), c[k], a);
+        s = __ffma2_rn(make_float2(wyz, wyz), a, s);
     }
 };

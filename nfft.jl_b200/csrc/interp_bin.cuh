@@ -169,14 +169,14 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                     for (int i = 0; i < W; i++) {
                         C c = make_c<T>(0, 0);
                         if (rowok) c = row[i];
-                        win_row[p].set(i, c.x, c.y);
+                        win_row[p].set(i, c);
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < W; i++) {
                         C c = make_c<T>(0, 0);
                         if (rowok && o0 + i < PX) c = row[i];
-                        win_row[p].set(i, c.x, c.y);
+                        win_row[p].set(i, c);
                     }
                 }
             }
@@ -199,7 +199,7 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                 T v[2 * RND];
 #pragma unroll
                 for (int n = 0; n < RND; n++) {
-                    T sx = (T)0, sy = (T)0;
+                    C sn = make_c<T>(0, 0);
                     if (n < nn) {                                           // warp-uniform
                         const T* rn = myrec + n * RW;
                         T wx[W];
@@ -210,13 +210,11 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                             if (NP * 32 == ROWS || lane + 32 * p < ROWS) {
                                 const T wyp = (32 % W == 0) ? wy : rn[W + rowy[p]];
                                 const T wyz = wyp * rn[2 * W + rowz[p]];
-                                T a, b;
-                                win_row[p].dot(wx, a, b);
-                                sx = tfma(wyz, a, sx); sy = tfma(wyz, b, sy);
+                                win_row[p].dot_acc(wx, wyz, sn);
                             }
                         }
                     }
-                    v[2 * n] = sx; v[2 * n + 1] = sy;
+                    v[2 * n] = sn.x; v[2 * n + 1] = sn.y;
                 }
                 // fold the round: value 2n / 2n+1 = real / imaginary part of node n
                 int idx;

@@ -189,7 +189,7 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                                 const T wy = rn[W + rowy[p]];
                                 NFFTB_EMU_ALIGNED(rn + 2 * W, sizeof(C));
                                 const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz[p]];
-                                acc[p].axpy(wx, wy * vz.x, wy * vz.y);
+                                acc[p].axpy(wx, wy, vz);
                             }
                         }
                     }
@@ -203,11 +203,11 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                         C* row = P + (Z * PL + Y * PXp + o0);
                         if (o0 + W <= PX) {                               // warp-uniform: all but the last bin of a row
 #pragma unroll
-                            for (int i = 0; i < W; i++) { C c = row[i]; c.x += acc[p].re(i); c.y += acc[p].im(i); row[i] = c; }
+                            for (int i = 0; i < W; i++) { C c = row[i]; acc[p].add_to(c, i); row[i] = c; }
                         } else {
 #pragma unroll
                             for (int i = 0; i < W; i++)
-                                if (o0 + i < PX) { C c = row[i]; c.x += acc[p].re(i); c.y += acc[p].im(i); row[i] = c; }
+                                if (o0 + i < PX) { C c = row[i]; acc[p].add_to(c, i); row[i] = c; }
                         }
                     }
                 }
