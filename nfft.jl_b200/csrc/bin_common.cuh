@@ -12,7 +12,7 @@
 #define NFFTB_EMU_ALIGNED(ptr, bytes)
 #endif
 
-#define NFFTB_BIN_MAXKEYS 256
+#define NFFTB_BIN_MAXKEYS 512
 #define NFFTB_BIN_WARPS 8
 #define NFFTB_BIN_ROUND 8          // nodes whose weights are evaluated together (lane = node * 3 + dim)
 
@@ -22,7 +22,9 @@ struct BinGeom {
     int G;             // first-tap positions per bin and dimension (the last bin of a period of W holds fewer)
     int S;             // colour stride in bins: windows of bins i and i + S are disjoint
     int nbin[3];       // bins per dimension (bin_of(bs - 1) + 1)
-    int nkeys;         // nbin[0] * nbin[1] * nbin[2]  (<= NFFTB_BIN_MAXKEYS)
+    int maxit;         // spreader: bins of one colour a warp may have to take, ceil(max bins per colour / warps)
+    int nkeys;         // spreader sort keys: (warp, colour, turn) = warps * S^3 * maxit  (<= NFFTB_BIN_MAXKEYS)
+    int ikeys;         // interpolator sort keys: (warp, turn) = warps * ceil(bins / warps)  (<= NFFTB_BIN_MAXKEYS)
     int PXp, PL;       // row pitch / plane pitch of the padded tile in shared memory (cells), bank-conflict free
     int PNs;           // cells of the shared-memory tile (PL * PZ, even)
 };
@@ -82,9 +84,16 @@ template <typename T, int MT, int W> inline bool bin_make_geom(const int* bs, Bi
     } rem{bs, bg};
     bg.G = G;
     bg.S = (W + G - 1) / G;
-    bg.nkeys = 1;
-    for (int d = 0; d < 3; d++) { bg.nbin[d] = bin_of<W, G>(bs[d] - 1) + 1; bg.nkeys *= bg.nbin[d]; }
-    if (bg.nkeys > NFFTB_BIN_MAXKEYS) return false;
+    int nbins = 1, percol = 1;
+    for (int d = 0; d < 3; d++) {
+        bg.nbin[d] = bin_of<W, G>(bs[d] - 1) + 1;
+        nbins *= bg.nbin[d];
+        percol *= (bg.nbin[d] + bg.S - 1) / bg.S;               // bins of the fullest colour along d
+    }
+    bg.maxit = (percol + NFFTB_BIN_WARPS - 1) / NFFTB_BIN_WARPS;
+    bg.nkeys = NFFTB_BIN_WARPS * bg.S * bg.S * bg.S * bg.maxit;
+    bg.ikeys = NFFTB_BIN_WARPS * ((nbins + NFFTB_BIN_WARPS - 1) / NFFTB_BIN_WARPS);
+    if (bg.nkeys > NFFTB_BIN_MAXKEYS || bg.ikeys > NFFTB_BIN_MAXKEYS) return false;
     const int PX = bs[0] + L, PY = bs[1] + L, PZ = bs[2] + L;
     int best = 1 << 30, bdeg = 1 << 30;
     bg.PXp = PX; bg.PL = PX * PY;
@@ -99,12 +108,13 @@ template <typename T, int MT, int W> inline bool bin_make_geom(const int* bs, Bi
     return true;
 }
 
-// Stable counting sort of a staged chunk by bin.  On entry key[0, nc) holds the bin of every staged node and
+// Stable counting sort of a staged chunk by key (a key names a bin and, through its leading digits, the warp that
+// will process it, so that a warp's nodes end up contiguous).  On entry key[0, nc) holds the key of every staged node and
 // cntw[NWARP * nkeys] is zero (both visible to the CTA); on exit order[bin_start[k] .. bin_start[k+1]) lists the
 // chunk-local ids of bin k in ascending order and cntw is dead.  No atomics: every warp ranks its own contiguous
 // range with __match_any_sync, so the order -- and with it every floating-point sum -- is reproducible.
 template <int CH, int NWARP>
-__device__ __forceinline__ void bin_sort_chunk(int nc, int nkeys, const unsigned char* key, unsigned char* rnk,
+__device__ __forceinline__ void bin_sort_chunk(int nc, int nkeys, const unsigned short* key, unsigned char* rnk,
                                                unsigned short* cntw, unsigned short* bin_start, unsigned short* order)
 {
     constexpr int NTHR = NWARP * 32, CW = CH / NWARP;       // CW: nodes ranked by one warp
@@ -133,14 +143,14 @@ __device__ __forceinline__ void bin_sort_chunk(int nc, int nkeys, const unsigned
     }
     __syncthreads();
     // (2) per bin: exclusive offsets of the warps' ranges, and the bin's node count
-    if (threadIdx.x < nkeys) {
+    for (int k = threadIdx.x; k < nkeys; k += NTHR) {
         int run = 0;
         for (int w = 0; w < NWARP; w++) {
-            const int c = cntw[w * nkeys + threadIdx.x];
-            cntw[w * nkeys + threadIdx.x] = (unsigned short)run;
+            const int c = cntw[w * nkeys + k];
+            cntw[w * nkeys + k] = (unsigned short)run;
             run += c;
         }
-        bin_start[threadIdx.x] = (unsigned short)run;
+        bin_start[k] = (unsigned short)run;
     }
     __syncthreads();
     // (3) exclusive scan of the bin counts by warp 0 (NFFTB_BIN_MAXKEYS / 32 bins per lane)

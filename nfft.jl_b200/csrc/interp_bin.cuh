@@ -14,7 +14,7 @@ template <typename T, int MT, int W> struct InterpBinLayout {
     using C = typename Cplx<T>::type;
     static constexpr int L = 2 * MT;
     static constexpr int G = W - L + 1;
-    static constexpr int RW = 4 * W;                       // record: wx[W] | wy[W] | wz[W] | pad
+    static constexpr int RW = 4 * W;                       // record: wx[W] | wy[W] | wz[W] | window origin (3 ints), pad
     static constexpr int ROWS = W * W, NP = (ROWS + 31) / 32;
     static bool make(const int* bs, BinGeom& bg) { return bin_make_geom<T, MT, W>(bs, bg); }
     static size_t bytes(const BinGeom& bg)
@@ -24,7 +24,7 @@ template <typename T, int MT, int W> struct InterpBinLayout {
         b += sizeof(T) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW;             // weight records (sort counters alias them)
         b += sizeof(T) * NFFTB_BIN_WARPS * 2 * NFFTB_BIN_ROUND;              // reduced results of a round
         b += sizeof(T) * 3 * CH + sizeof(int) * CH;                          // staged coordinates and destinations
-        b += 2 * CH + CH + CH;                                               // order (u16), key (u8), rank (u8)
+        b += 2 * CH + 2 * CH + CH;                                           // order (u16), key (u16), rank (u8)
         b += 2 * (NFFTB_BIN_MAXKEYS + 8);                                    // bin_start (u16)
         return b + 16;
     }
@@ -83,8 +83,8 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     int* s_j = reinterpret_cast<int*>(s_x + 3 * CH);                                // [CH] destination (caller's node id)
     unsigned short* order = reinterpret_cast<unsigned short*>(s_j + CH);            // [CH]
     unsigned short* bin_start = order + CH;                                         // [nkeys + 1]
-    unsigned char* key = reinterpret_cast<unsigned char*>(bin_start + NFFTB_BIN_MAXKEYS + 8);   // [CH]
-    unsigned char* rnk = key + CH;                                                  // [CH]
+    unsigned short* key = bin_start + NFFTB_BIN_MAXKEYS + 8;                        // [CH] (warp, turn) of the node's bin
+    unsigned char* rnk = reinterpret_cast<unsigned char*>(key + CH);                // [CH]
 
     const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
     const int tile_id = item[0];
@@ -94,7 +94,7 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
     const int cx0 = tx * geo.bs[0], cy0 = ty * geo.bs[1], cz0 = tz * geo.bs[2];     // first core cell
     const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
-    const int PXp = bg.PXp, PL = bg.PL, nkeys = bg.nkeys;
+    const int PXp = bg.PXp, PL = bg.PL, nkeys = bg.ikeys, turns = bg.ikeys / NWARP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     g += (long long)blockIdx.y * geo.gsz;
     fhat += (long long)blockIdx.y * M;
@@ -139,7 +139,9 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
             const int b0 = bin_of<W, G>(node_cell<T>(x0, geo.Nt[0], ks) - cx0);
             const int b1 = bin_of<W, G>(node_cell<T>(x1, geo.Nt[1], ks) - cy0);
             const int b2 = bin_of<W, G>(node_cell<T>(x2, geo.Nt[2], ks) - cz0);
-            key[q] = (unsigned char)((b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0);
+            // bins are dealt to the warps round-robin; the key (warp, turn) makes the nodes of one warp contiguous
+            const int kb = (b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0;
+            key[q] = (unsigned short)((kb % NWARP) * turns + kb / NWARP);
             s_x[q * 3 + 0] = x0; s_x[q * 3 + 1] = x1; s_x[q * 3 + 2] = x2;
             s_j[q] = perm[i];
         }
@@ -147,61 +149,70 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
         bin_sort_chunk<CH, NWARP>(nc, nkeys, key, rnk, cntw, bin_start, order);
         if (cbase == n_lo) { bin_copy_wait(); __syncthreads(); }            // tile resident
 
-        int kk = -1;
-        for (int b2 = 0; b2 < bg.nbin[2]; b2++)
-        for (int b1 = 0; b1 < bg.nbin[1]; b1++)
-        for (int b0 = 0; b0 < bg.nbin[0]; b0++) {
-            kk++;                                                           // bin key, dealt to the warps round-robin
-            if ((kk & (NWARP - 1)) != warp) continue;
-            const int lo = bin_start[kk], hi = bin_start[kk + 1];
+        // This warp's nodes are contiguous in `order` (bin after bin); weight records are evaluated RND nodes at a time
+        // along that list, so a round may cover several sparse bins.
+        const int wl1 = bin_start[(warp + 1) * turns];
+        int rbase = -RND;                                                   // list index of the resident round
+        for (int t = 0; t < turns; t++) {
+            const int lo = bin_start[warp * turns + t], hi = bin_start[warp * turns + t + 1];
             if (hi <= lo) continue;                                         // warp-uniform
-            const int o0 = 1 + bin_first<W, G>(b0), o1 = 1 + bin_first<W, G>(b1), o2 = 1 + bin_first<W, G>(b2);    // window origin, padded-tile coordinates
-            const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
-            // the bin's window -> registers (cells beyond the padded tile meet zero weights only)
             BinRow<T, W> win_row[NP];
+            for (int i = lo; i < hi;) {
+                if (i >= rbase + RND) {                                     // warp-uniform: next round of records
+                    __syncwarp();                                           // the previous round has been read
+                    rbase = i;
+                    if (wn < min(RND, wl1 - rbase)) {                       // weights of (node wn of the round, dimension wd)
+                        const int q = order[rbase + wn];
+                        T ks;
+                        const int c = node_cell<T>(s_x[q * 3 + wd], wNt, ks);
+                        T w[L];
+                        eval_taps<T, MT>(win, pp, ks, c, w);
+                        const int lc = c - wc0;                             // first tap at padded coordinate lc + 1
+                        const int wo = 1 + bin_first<W, G>(bin_of<W, G>(lc));
+                        const int dl = lc + 1 - wo;                         // first tap inside the window, in [0, G)
+                        reinterpret_cast<int*>(myrec + wn * RW + 3 * W)[wd] = wo;
+                        T* rn = myrec + wn * RW + wd * W;                   // 2m taps at [dl, dl + 2m), zeros elsewhere
 #pragma unroll
-            for (int p = 0; p < NP; p++) {
-                const int Y = o1 + rowy[p], Z = o2 + rowz[p];
-                const bool rowok = (NP * 32 == ROWS || lane + 32 * p < ROWS) && Y < PY && Z < PZ;
-                const C* row = P + (Z * PL + Y * PXp + o0);
-                if (o0 + W <= PX) {                                         // warp-uniform: all but the last bin of a row
+                        for (int l = 0; l < L; l++) rn[dl + l] = w[l];
 #pragma unroll
-                    for (int i = 0; i < W; i++) {
-                        C c = make_c<T>(0, 0);
-                        if (rowok) c = row[i];
-                        win_row[p].set(i, c);
+                        for (int j = 0; j < W - L; j++) rn[j < dl ? j : j + L] = (T)0;
                     }
-                } else {
+                    __syncwarp();
+                }
+                const int r0 = i - rbase;                                   // first record of this segment
+                const int nn = min(hi, rbase + RND) - i;                    // nodes of the bin inside the resident round
+                if (i == lo) {
+                    // the bin's window -> registers (cells beyond the padded tile meet zero weights only)
+                    const int* ro = reinterpret_cast<const int*>(myrec + r0 * RW + 3 * W);
+                    const int o0 = ro[0], o1 = ro[1], o2 = ro[2];           // window origin, padded-tile coordinates
 #pragma unroll
-                    for (int i = 0; i < W; i++) {
-                        C c = make_c<T>(0, 0);
-                        if (rowok && o0 + i < PX) c = row[i];
-                        win_row[p].set(i, c);
+                    for (int p = 0; p < NP; p++) {
+                        const int Y = o1 + rowy[p], Z = o2 + rowz[p];
+                        const bool rowok = (NP * 32 == ROWS || lane + 32 * p < ROWS) && Y < PY && Z < PZ;
+                        const C* row = P + (Z * PL + Y * PXp + o0);
+                        if (o0 + W <= PX) {                                 // warp-uniform: all but the last bin of a row
+#pragma unroll
+                            for (int k = 0; k < W; k++) {
+                                C c = make_c<T>(0, 0);
+                                if (rowok) c = row[k];
+                                win_row[p].set(k, c);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < W; k++) {
+                                C c = make_c<T>(0, 0);
+                                if (rowok && o0 + k < PX) c = row[k];
+                                win_row[p].set(k, c);
+                            }
+                        }
                     }
                 }
-            }
-            for (int r0 = lo; r0 < hi; r0 += RND) {
-                const int nn = min(RND, hi - r0);
-                if (wn < nn) {                                              // weights of (node wn, dimension wd)
-                    const int q = order[r0 + wn];
-                    T ks;
-                    const int c = node_cell<T>(s_x[q * 3 + wd], wNt, ks);
-                    T w[L];
-                    eval_taps<T, MT>(win, pp, ks, c, w);
-                    const int dl = c - wc0 + 1 - wo;                        // first tap inside the window, in [0, G)
-                    T* rn = myrec + wn * RW + wd * W;                       // 2m taps at [dl, dl + 2m), zeros elsewhere
-#pragma unroll
-                    for (int l = 0; l < L; l++) rn[dl + l] = w[l];
-#pragma unroll
-                    for (int j = 0; j < W - L; j++) rn[j < dl ? j : j + L] = (T)0;
-                }
-                __syncwarp();
                 T v[2 * RND];
 #pragma unroll
                 for (int n = 0; n < RND; n++) {
                     C sn = make_c<T>(0, 0);
                     if (n < nn) {                                           // warp-uniform
-                        const T* rn = myrec + n * RW;
+                        const T* rn = myrec + (r0 + n) * RW;
                         T wx[W];
                         bin_load_row<T, W>(rn, wx);
                         const T wy = rn[W + rowy[0]];                       // rowy[p] is the same for every pass when 32 % W == 0
@@ -216,7 +227,7 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                     }
                     v[2 * n] = sn.x; v[2 * n + 1] = sn.y;
                 }
-                // fold the round: value 2n / 2n+1 = real / imaginary part of node n
+                // fold the segment: value 2n / 2n+1 = real / imaginary part of its node n
                 int idx;
                 if (nn > RND / 2) {
                     const T tot = bin_halving_reduce<T, 2 * RND>(v, lane, idx);
@@ -229,8 +240,9 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
                     if ((lane & (32 / RND - 1)) == 0) myres[idx] = tot;
                 }
                 __syncwarp();
-                if (lane < nn) fhat[s_j[order[r0 + lane]]] = make_c<T>(myres[2 * lane], myres[2 * lane + 1]);
+                if (lane < nn) fhat[s_j[order[i + lane]]] = make_c<T>(myres[2 * lane], myres[2 * lane + 1]);
                 __syncwarp();
+                i += nn;
             }
         }
         __syncthreads();                                                    // staging arrays free for the next chunk

@@ -836,7 +836,7 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
         switch (p->m) {
             case 2: r = launch_bin3d<T, 2, 8>(p, fhat, g, B, t_lo, t_hi); break;
             case 3: r = launch_bin3d<T, 3, 8>(p, fhat, g, B, t_lo, t_hi); break;
-            case 4: r = launch_bin3d<T, 4, 10>(p, fhat, g, B, t_lo, t_hi); break;
+            case 4: if constexpr (sizeof(T) == 4) r = launch_bin3d<T, 4, 10>(p, fhat, g, B, t_lo, t_hi); break;   // Float64: tile + records exceed 227 KB
             default: break;
         }
         if (r >= 0) return r;

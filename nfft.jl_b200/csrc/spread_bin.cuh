@@ -30,7 +30,7 @@ template <typename T, int MT, int W> struct BinLayout {
     using C = typename Cplx<T>::type;
     static constexpr int L = 2 * MT;
     static constexpr int G = W - L + 1;
-    static constexpr int RW = 4 * W;                       // record: wx[W] | wy[W] | (wz * v)[W] interleaved re, im
+    static constexpr int RW = 4 * W + 16 / (int)sizeof(T); // record: wx[W] | wy[W] | (wz * v)[W] re, im | window origin (3 ints)
     static constexpr int ROWS = W * W, NP = (ROWS + 31) / 32;
     static_assert(G >= 1, "window narrower than the footprint");
 
@@ -41,7 +41,7 @@ template <typename T, int MT, int W> struct BinLayout {
         size_t b = sizeof(C) * (size_t)bg.PNs;                               // padded tile
         b += sizeof(T) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW;             // weight records (sort counters alias them)
         b += sizeof(C) * CH + sizeof(T) * 3 * CH;                            // staged values and coordinates
-        b += 2 * CH + CH + CH;                                               // order (u16), key (u8), rank (u8)
+        b += 2 * CH + 2 * CH + CH;                                           // order (u16), key (u16), rank (u8)
         b += 2 * (NFFTB_BIN_MAXKEYS + 8);                                    // bin_start (u16)
         return b + 16;
     }
@@ -58,6 +58,7 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     using BL = BinLayout<T, MT, W>;
     constexpr int L = BL::L, G = BL::G, RW = BL::RW, NP = BL::NP, ROWS = BL::ROWS;
     constexpr int NWARP = NFFTB_BIN_WARPS, NTHR = NWARP * 32, CH = BinChunk<T>::value, RND = NFFTB_BIN_ROUND;
+    constexpr int S = (W + G - 1) / G, NPH = S * S * S;     // colours per dimension / per tile
     static_assert(3 * RND <= 32, "one lane per (node, dimension)");
     static_assert(sizeof(unsigned short) * NWARP * NFFTB_BIN_MAXKEYS <= sizeof(T) * NWARP * RND * RW, "counters alias the records");
 
@@ -69,8 +70,8 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     T* s_x = reinterpret_cast<T*>(s_v + CH);                                        // [CH][3]
     unsigned short* order = reinterpret_cast<unsigned short*>(s_x + 3 * CH);        // [CH] bin-sorted chunk-local ids
     unsigned short* bin_start = order + CH;                                         // [nkeys + 1]
-    unsigned char* key = reinterpret_cast<unsigned char*>(bin_start + NFFTB_BIN_MAXKEYS + 8);   // [CH]
-    unsigned char* rnk = key + CH;                                                  // [CH]
+    unsigned short* key = bin_start + NFFTB_BIN_MAXKEYS + 8;                        // [CH] (warp, colour, turn) of the node's bin
+    unsigned char* rnk = reinterpret_cast<unsigned char*>(key + CH);                // [CH]
 
     const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
     const int tile_id = item[0];
@@ -126,7 +127,12 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
                 const int b0 = bin_of<W, G>(node_cell<T>(rx[k][0], geo.Nt[0], ks) - cx0);
                 const int b1 = bin_of<W, G>(node_cell<T>(rx[k][1], geo.Nt[1], ks) - cy0);
                 const int b2 = bin_of<W, G>(node_cell<T>(rx[k][2], geo.Nt[2], ks) - cz0);
-                key[q] = (unsigned char)((b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0);
+                // colour = (b mod S) per dimension; the bins of a colour are dealt to the warps round-robin ("slot"); the
+                // key (warp, colour, turn) makes the nodes of one warp contiguous, in the order the warp needs them
+                const int p0 = b0 % S, p1 = b1 % S, p2 = b2 % S;
+                const int A0 = (bg.nbin[0] - p0 + S - 1) / S, A1 = (bg.nbin[1] - p1 + S - 1) / S;
+                const int slot = ((b2 / S) * A1 + b1 / S) * A0 + b0 / S;
+                key[q] = (unsigned short)(((slot % NWARP) * NPH + (p2 * S + p1) * S + p0) * bg.maxit + slot / NWARP);
                 s_x[q * 3 + 0] = rx[k][0]; s_x[q * 3 + 1] = rx[k][1]; s_x[q * 3 + 2] = rx[k][2];
                 s_v[q] = rv[k];
             }
@@ -134,66 +140,69 @@ k_spread_bin3d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
         __syncthreads();
         bin_sort_chunk<CH, NWARP>(nc, nkeys, key, rnk, cntw, bin_start, order);
 
-        // ---- accumulate: S^3 colours, the bins of one colour have disjoint windows and run on different warps
-        constexpr int S = (W + G - 1) / G;
-        for (int ph = 0; ph < S * S * S; ph++) {
-            const int p0 = ph % S, p1 = (ph / S) % S, p2 = ph / (S * S);
-            // the bins of this colour, dealt to the warps round-robin (a 16^3 tile has 2 x 2 x 2 per colour: one each)
-            int slot = 0;
-            for (int b2 = p2; b2 < bg.nbin[2]; b2 += S)
-            for (int b1 = p1; b1 < bg.nbin[1]; b1 += S)
-            for (int b0 = p0; b0 < bg.nbin[0]; b0 += S) {
-                if (((slot++) & (NWARP - 1)) != warp) continue;
-                const int kk = (b2 * bg.nbin[1] + b1) * bg.nbin[0] + b0;
+        // ---- accumulate: S^3 colours; the bins of one colour have disjoint windows and run on different warps.
+        //      This warp's nodes are contiguous in `order` (colour-major), so the weight records are evaluated RND
+        //      nodes at a time along that list -- a round may run ahead into the bins of later colours, which keeps
+        //      the (node, dimension) lanes busy even when a bin holds two or three nodes.
+        const int wl1 = bin_start[(warp + 1) * NPH * bg.maxit];             // end of this warp's node list
+        int rbase = -RND;                                                   // list index of the resident round
+        for (int ph = 0; ph < NPH; ph++) {
+            for (int it = 0; it < bg.maxit; it++) {
+                const int kk = (warp * NPH + ph) * bg.maxit + it;
                 const int lo = bin_start[kk], hi = bin_start[kk + 1];
                 if (hi <= lo) continue;                                   // warp-uniform
-                // window origin in padded-tile coordinates: first tap of the bin's first position (cell b*G -> 1 + b*G)
-                const int o0 = 1 + bin_first<W, G>(b0), o1 = 1 + bin_first<W, G>(b1), o2 = 1 + bin_first<W, G>(b2);
-                const int wo = wd == 0 ? o0 : (wd == 1 ? o1 : o2);
                 BinRow<T, W> acc[NP];
 #pragma unroll
                 for (int p = 0; p < NP; p++) acc[p].zero();
-                for (int r0 = lo; r0 < hi; r0 += RND) {
-                    const int nn = min(RND, hi - r0);
-                    if (wn < nn) {                                        // weights of (node wn, dimension wd)
-                        const int q = order[r0 + wn];
-                        T ks;
-                        const int c = node_cell<T>(s_x[q * 3 + wd], wNt, ks);
-                        T w[L];
-                        eval_taps<T, MT>(win, pp, ks, c, w);
-                        const int dl = c - wc0 + 1 - wo;                  // first tap inside the window, in [0, G)
-                        T* rn = myrec + wn * RW;
-                        // the 2m taps at window positions [dl, dl + 2m), zeros in the other W - 2m positions
-                        if (wd < 2) {
+                int o0 = 0, o1 = 0, o2 = 0;                               // window origin of the bin, padded-tile coordinates
+                for (int i = lo; i < hi; i++) {
+                    if (i >= rbase + RND) {                               // warp-uniform: next round of records
+                        __syncwarp();                                     // the previous round has been read
+                        rbase = i;
+                        if (wn < min(RND, wl1 - rbase)) {                 // weights of (node wn of the round, dimension wd)
+                            const int q = order[rbase + wn];
+                            T ks;
+                            const int c = node_cell<T>(s_x[q * 3 + wd], wNt, ks);
+                            T w[L];
+                            eval_taps<T, MT>(win, pp, ks, c, w);
+                            const int lc = c - wc0;                       // first tap at padded coordinate lc + 1
+                            const int wo = 1 + bin_first<W, G>(bin_of<W, G>(lc));
+                            const int dl = lc + 1 - wo;                   // first tap inside the window, in [0, G)
+                            T* rn = myrec + wn * RW;
+                            reinterpret_cast<int*>(rn + 4 * W)[wd] = wo;
+                            // the 2m taps at window positions [dl, dl + 2m), zeros in the other W - 2m positions
+                            if (wd < 2) {
 #pragma unroll
-                            for (int l = 0; l < L; l++) rn[wd * W + dl + l] = w[l];
+                                for (int l = 0; l < L; l++) rn[wd * W + dl + l] = w[l];
 #pragma unroll
-                            for (int j = 0; j < W - L; j++) rn[wd * W + (j < dl ? j : j + L)] = (T)0;
-                        } else {
-                            const C v = s_v[q];
-                            C* rz = reinterpret_cast<C*>(rn + 2 * W);
+                                for (int j = 0; j < W - L; j++) rn[wd * W + (j < dl ? j : j + L)] = (T)0;
+                            } else {
+                                const C v = s_v[q];
+                                C* rz = reinterpret_cast<C*>(rn + 2 * W);
 #pragma unroll
-                            for (int l = 0; l < L; l++) rz[dl + l] = make_c<T>(w[l] * v.x, w[l] * v.y);
+                                for (int l = 0; l < L; l++) rz[dl + l] = make_c<T>(w[l] * v.x, w[l] * v.y);
 #pragma unroll
-                            for (int j = 0; j < W - L; j++) rz[j < dl ? j : j + L] = make_c<T>(0, 0);
-                        }
-                    }
-                    __syncwarp();
-                    for (int n = 0; n < nn; n++) {
-                        const T* rn = myrec + n * RW;
-                        T wx[W];
-                        bin_load_row<T, W>(rn, wx);
-#pragma unroll
-                        for (int p = 0; p < NP; p++) {
-                            if (NP * 32 == ROWS || lane + 32 * p < ROWS) {
-                                const T wy = rn[W + rowy[p]];
-                                NFFTB_EMU_ALIGNED(rn + 2 * W, sizeof(C));
-                                const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz[p]];
-                                acc[p].axpy(wx, wy, vz);
+                                for (int j = 0; j < W - L; j++) rz[j < dl ? j : j + L] = make_c<T>(0, 0);
                             }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
+                    const T* rn = myrec + (i - rbase) * RW;
+                    if (i == lo) {
+                        const int* ro = reinterpret_cast<const int*>(rn + 4 * W);
+                        o0 = ro[0]; o1 = ro[1]; o2 = ro[2];
+                    }
+                    T wx[W];
+                    bin_load_row<T, W>(rn, wx);
+#pragma unroll
+                    for (int p = 0; p < NP; p++) {
+                        if (NP * 32 == ROWS || lane + 32 * p < ROWS) {
+                            const T wy = rn[W + rowy[p]];
+                            NFFTB_EMU_ALIGNED(rn + 2 * W, sizeof(C));
+                            const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz[p]];
+                            acc[p].axpy(wx, wy, vz);
+                        }
+                    }
                 }
                 // one read-modify-write of the window (cells beyond the padded tile carry zero weights only)
 #pragma unroll

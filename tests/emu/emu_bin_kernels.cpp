@@ -205,6 +205,8 @@ int main()
     bad += run_case<float, 4, 10>("f32 m=4 (W=10) 32^3", n32, b16, 2000, 100, 1, 5);
     bad += run_case<double, 4, 10>("f64 m=4 (W=10) 32^3", n32, b16, 1200, 0, 1, 6);
     bad += run_case<float, 3, 8>("f32 m=3 thin tiles 16x16x8", nthin, bthin, 1500, 0, 1, 7);
+    const int nwide[3] = {64, 32, 32}, bwide[3] = {32, 16, 16};
+    bad += run_case<float, 3, 8>("f32 m=3 wide tiles 32x16x16 (two bins per warp and colour)", nwide, bwide, 3000, 300, 1, 10);
     bad += run_case<float, 3, 8>("f32 m=3 LINEAR lookup table", n32, b16, 1500, 0, 1, 8, NFFTB200_LINEAR);
     bad += run_case<double, 3, 8>("f64 m=3 FULL (exact Kaiser-Bessel)", n32, b16, 1500, 0, 1, 9, NFFTB200_FULL);
     printf(bad ? "FAILED\n" : "ALL OK\n");
