@@ -2,10 +2,11 @@
 //   replaces toBlock!/calcOneBlock!/calcOneNode! (/root/reference/src/convolution.jl:229-344) like k_interp_row3d.
 //
 // The transpose of spread_bin.cuh: k_interp_row3d reads (2m)^3 complex cells of shared memory per node; here the
-// nodes of the tile are counting-sorted into bins of G^3 first-tap positions (bin_common.cuh), one warp loads the W^3
-// window of a bin into REGISTERS once (lane r owns the x-row (y, z) = (r % W, r / W), W complex cells per pass) and
-// every node of the bin is a register dot product with its window-aligned weights (zeros outside its 2m taps)
-// followed by a butterfly reduction that folds the 8 nodes of a round together (2 shuffles per node instead of 10).
+// nodes of the tile are counting-sorted into bins of up to G^3 first-tap positions (bin_common.cuh) with the owning
+// warp in the sort key, so every warp walks a contiguous node list, 8 nodes per round: the W^3 window of a bin is
+// loaded into REGISTERS when the list enters the bin (lane r owns the x-row (y, z) = (r % W, r / W), W complex cells
+// per pass), every node is a register dot product with its window-aligned weights (zeros outside its 2m taps), and
+// one butterfly reduction folds the 8 nodes of a round together (2 shuffles per node instead of 10).
 // The tile is read-only, so bins need no colouring and no CTA barrier separates them.
 #pragma once
 #include "bin_common.cuh"
@@ -149,101 +150,94 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
         bin_sort_chunk<CH, NWARP>(nc, nkeys, key, rnk, cntw, bin_start, order);
         if (cbase == n_lo) { bin_copy_wait(); __syncthreads(); }            // tile resident
 
-        // This warp's nodes are contiguous in `order` (bin after bin); weight records are evaluated RND nodes at a time
-        // along that list, so a round may cover several sparse bins.
-        const int wl1 = bin_start[(warp + 1) * turns];
-        int rbase = -RND;                                                   // list index of the resident round
-        for (int t = 0; t < turns; t++) {
-            const int lo = bin_start[warp * turns + t], hi = bin_start[warp * turns + t + 1];
-            if (hi <= lo) continue;                                         // warp-uniform
-            BinRow<T, W> win_row[NP];
-            for (int i = lo; i < hi;) {
-                if (i >= rbase + RND) {                                     // warp-uniform: next round of records
-                    __syncwarp();                                           // the previous round has been read
-                    rbase = i;
-                    if (wn < min(RND, wl1 - rbase)) {                       // weights of (node wn of the round, dimension wd)
-                        const int q = order[rbase + wn];
-                        T ks;
-                        const int c = node_cell<T>(s_x[q * 3 + wd], wNt, ks);
-                        T w[L];
-                        eval_taps<T, MT>(win, pp, ks, c, w);
-                        const int lc = c - wc0;                             // first tap at padded coordinate lc + 1
-                        const int wo = 1 + bin_first<W, G>(bin_of<W, G>(lc));
-                        const int dl = lc + 1 - wo;                         // first tap inside the window, in [0, G)
-                        reinterpret_cast<int*>(myrec + wn * RW + 3 * W)[wd] = wo;
-                        T* rn = myrec + wn * RW + wd * W;                   // 2m taps at [dl, dl + 2m), zeros elsewhere
+        // This warp's nodes are contiguous in `order`, bin after bin.  The warp walks that list RND nodes at a time: one
+        // evaluation of the weight records, one register dot product per node -- the window registers are reloaded
+        // whenever a node's window origin differs from the resident one, i.e. at the first node of every bin -- and
+        // one butterfly reduction and one store per round, however many sparse bins the round covers.
+        const int wl0 = bin_start[warp * turns], wl1 = bin_start[(warp + 1) * turns];
+        BinRow<T, W> win_row[NP];
+        int c0 = -1, c1 = -1, c2 = -1;                                      // origin of the resident window
+        for (int rbase = wl0; rbase < wl1; rbase += RND) {
+            const int nn = min(RND, wl1 - rbase);
+            if (wn < nn) {                                                  // weights of (node wn of the round, dimension wd)
+                const int q = order[rbase + wn];
+                T ks;
+                const int c = node_cell<T>(s_x[q * 3 + wd], wNt, ks);
+                T w[L];
+                eval_taps<T, MT>(win, pp, ks, c, w);
+                const int lc = c - wc0;                                     // first tap at padded coordinate lc + 1
+                const int wo = 1 + bin_first<W, G>(bin_of<W, G>(lc));
+                const int dl = lc + 1 - wo;                                 // first tap inside the window, in [0, G)
+                reinterpret_cast<int*>(myrec + wn * RW + 3 * W)[wd] = wo;
+                T* rn = myrec + wn * RW + wd * W;                           // 2m taps at [dl, dl + 2m), zeros elsewhere
 #pragma unroll
-                        for (int l = 0; l < L; l++) rn[dl + l] = w[l];
+                for (int l = 0; l < L; l++) rn[dl + l] = w[l];
 #pragma unroll
-                        for (int j = 0; j < W - L; j++) rn[j < dl ? j : j + L] = (T)0;
-                    }
-                    __syncwarp();
-                }
-                const int r0 = i - rbase;                                   // first record of this segment
-                const int nn = min(hi, rbase + RND) - i;                    // nodes of the bin inside the resident round
-                if (i == lo) {
-                    // the bin's window -> registers (cells beyond the padded tile meet zero weights only)
-                    const int* ro = reinterpret_cast<const int*>(myrec + r0 * RW + 3 * W);
+                for (int j = 0; j < W - L; j++) rn[j < dl ? j : j + L] = (T)0;
+            }
+            __syncwarp();
+            T v[2 * RND];
+#pragma unroll
+            for (int n = 0; n < RND; n++) {
+                C sn = make_c<T>(0, 0);
+                if (n < nn) {                                               // warp-uniform
+                    const T* rn = myrec + n * RW;
+                    const int* ro = reinterpret_cast<const int*>(rn + 3 * W);
                     const int o0 = ro[0], o1 = ro[1], o2 = ro[2];           // window origin, padded-tile coordinates
-#pragma unroll
-                    for (int p = 0; p < NP; p++) {
-                        const int Y = o1 + rowy[p], Z = o2 + rowz[p];
-                        const bool rowok = (NP * 32 == ROWS || lane + 32 * p < ROWS) && Y < PY && Z < PZ;
-                        const C* row = P + (Z * PL + Y * PXp + o0);
-                        if (o0 + W <= PX) {                                 // warp-uniform: all but the last bin of a row
-#pragma unroll
-                            for (int k = 0; k < W; k++) {
-                                C c = make_c<T>(0, 0);
-                                if (rowok) c = row[k];
-                                win_row[p].set(k, c);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < W; k++) {
-                                C c = make_c<T>(0, 0);
-                                if (rowok && o0 + k < PX) c = row[k];
-                                win_row[p].set(k, c);
-                            }
-                        }
-                    }
-                }
-                T v[2 * RND];
-#pragma unroll
-                for (int n = 0; n < RND; n++) {
-                    C sn = make_c<T>(0, 0);
-                    if (n < nn) {                                           // warp-uniform
-                        const T* rn = myrec + (r0 + n) * RW;
-                        T wx[W];
-                        bin_load_row<T, W>(rn, wx);
-                        const T wy = rn[W + rowy[0]];                       // rowy[p] is the same for every pass when 32 % W == 0
+                    if (o0 != c0 || o1 != c1 || o2 != c2) {                 // warp-uniform: first node of a bin
+                        c0 = o0; c1 = o1; c2 = o2;
+                        // the bin's window -> registers (cells beyond the padded tile meet zero weights only)
 #pragma unroll
                         for (int p = 0; p < NP; p++) {
-                            if (NP * 32 == ROWS || lane + 32 * p < ROWS) {
-                                const T wyp = (32 % W == 0) ? wy : rn[W + rowy[p]];
-                                const T wyz = wyp * rn[2 * W + rowz[p]];
-                                win_row[p].dot_acc(wx, wyz, sn);
+                            const int Y = o1 + rowy[p], Z = o2 + rowz[p];
+                            const bool rowok = (NP * 32 == ROWS || lane + 32 * p < ROWS) && Y < PY && Z < PZ;
+                            const C* row = P + (Z * PL + Y * PXp + o0);
+                            if (o0 + W <= PX) {                             // all but the last bin of a row
+#pragma unroll
+                                for (int k = 0; k < W; k++) {
+                                    C c = make_c<T>(0, 0);
+                                    if (rowok) c = row[k];
+                                    win_row[p].set(k, c);
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < W; k++) {
+                                    C c = make_c<T>(0, 0);
+                                    if (rowok && o0 + k < PX) c = row[k];
+                                    win_row[p].set(k, c);
+                                }
                             }
                         }
                     }
-                    v[2 * n] = sn.x; v[2 * n + 1] = sn.y;
-                }
-                // fold the segment: value 2n / 2n+1 = real / imaginary part of its node n
-                int idx;
-                if (nn > RND / 2) {
-                    const T tot = bin_halving_reduce<T, 2 * RND>(v, lane, idx);
-                    if ((lane & (32 / (2 * RND) - 1)) == 0) myres[idx] = tot;
-                } else {
-                    T h[RND];
+                    T wx[W];
+                    bin_load_row<T, W>(rn, wx);
+                    const T wy = rn[W + rowy[0]];                           // rowy[p] is the same for every pass when 32 % W == 0
 #pragma unroll
-                    for (int k = 0; k < RND; k++) h[k] = v[k];
-                    const T tot = bin_halving_reduce<T, RND>(h, lane, idx);
-                    if ((lane & (32 / RND - 1)) == 0) myres[idx] = tot;
+                    for (int p = 0; p < NP; p++) {
+                        if (NP * 32 == ROWS || lane + 32 * p < ROWS) {
+                            const T wyp = (32 % W == 0) ? wy : rn[W + rowy[p]];
+                            const T wyz = wyp * rn[2 * W + rowz[p]];
+                            win_row[p].dot_acc(wx, wyz, sn);
+                        }
+                    }
                 }
-                __syncwarp();
-                if (lane < nn) fhat[s_j[order[i + lane]]] = make_c<T>(myres[2 * lane], myres[2 * lane + 1]);
-                __syncwarp();
-                i += nn;
+                v[2 * n] = sn.x; v[2 * n + 1] = sn.y;
             }
+            // fold the round: value 2n / 2n+1 = real / imaginary part of its node n
+            int idx;
+            if (nn > RND / 2) {
+                const T tot = bin_halving_reduce<T, 2 * RND>(v, lane, idx);
+                if ((lane & (32 / (2 * RND) - 1)) == 0) myres[idx] = tot;
+            } else {
+                T h[RND];
+#pragma unroll
+                for (int k = 0; k < RND; k++) h[k] = v[k];
+                const T tot = bin_halving_reduce<T, RND>(h, lane, idx);
+                if ((lane & (32 / RND - 1)) == 0) myres[idx] = tot;
+            }
+            __syncwarp();
+            if (lane < nn) fhat[s_j[order[rbase + lane]]] = make_c<T>(myres[2 * lane], myres[2 * lane + 1]);
+            __syncwarp();                                                   // records and results free for the next round
         }
         __syncthreads();                                                    // staging arrays free for the next chunk
     }
