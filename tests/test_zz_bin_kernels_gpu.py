@@ -17,6 +17,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.xfail(strict=False, reason="experimental kernel_mode 7: verified by host emulation only so far")
 def test_bin_kernels_parity_on_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "try_bin_kernels.py")], cwd=ROOT,
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:])
     assert out.returncode == 0 and "PARITY OK" in out.stdout, (out.stdout + out.stderr)[-3000:]
