@@ -192,9 +192,34 @@ static int run_case(const char* name, const int Nt[3], const int bs[3], int M, i
     return ok ? 0 : 1;
 }
 
+// bin layout invariants for every tile edge 3..48: every first-tap position falls into a bin whose W-wide window
+// holds all its 2m taps, bins are contiguous and ordered, and bins of one colour (index distance a multiple of S) have
+// disjoint windows -- the property the barrier-separated colours of the spreader rely on
+template <int MT, int W> static int check_layout()
+{
+    constexpr int L = 2 * MT, G = W - L + 1, S = (W + G - 1) / G;
+    int bad = 0;
+    for (int bs = 3; bs <= 48; bs++) {
+        const int nbin = bin_of<W, G>(bs - 1) + 1;
+        int prev = 0;
+        for (int lc = 0; lc < bs; lc++) {
+            const int b = bin_of<W, G>(lc), first = bin_first<W, G>(b), dl = lc - first;
+            if (b < prev || b > prev + 1 || b >= nbin) bad++;
+            if (dl < 0 || dl >= G || dl + L > W) bad++;
+            prev = b;
+        }
+        for (int b = 0; b < nbin; b++)
+            for (int c = b + S; c < nbin; c += S)
+                if (bin_first<W, G>(c) - bin_first<W, G>(b) < W) bad++;
+    }
+    printf("bin layout m=%d W=%d (G=%d, S=%d): %s\n", MT, W, G, S, bad ? "FAIL" : "OK");
+    return bad;
+}
+
 int main()
 {
     int bad = 0;
+    bad += check_layout<2, 8>() + check_layout<3, 8>() + check_layout<4, 10>() + check_layout<1, 8>() + check_layout<5, 12>();
     const int n32[3] = {32, 32, 32}, b16[3] = {16, 16, 16};
     const int n40[3] = {40, 32, 48};
     const int nthin[3] = {32, 32, 16}, bthin[3] = {16, 16, 8};
@@ -205,6 +230,8 @@ int main()
     bad += run_case<float, 4, 10>("f32 m=4 (W=10) 32^3", n32, b16, 2000, 100, 1, 5);
     bad += run_case<double, 4, 10>("f64 m=4 (W=10) 32^3", n32, b16, 1200, 0, 1, 6);
     bad += run_case<float, 3, 8>("f32 m=3 thin tiles 16x16x8", nthin, bthin, 1500, 0, 1, 7);
+    const int nodd[3] = {24, 30, 28}, bodd[3] = {12, 10, 14};
+    bad += run_case<float, 3, 8>("f32 m=3 tiles 12x10x14 (not a multiple of the bin period)", nodd, bodd, 2500, 200, 1, 11);
     const int nwide[3] = {64, 32, 32}, bwide[3] = {32, 16, 16};
     bad += run_case<float, 3, 8>("f32 m=3 wide tiles 32x16x16 (two bins per warp and colour)", nwide, bwide, 3000, 300, 1, 10);
     bad += run_case<float, 3, 8>("f32 m=3 LINEAR lookup table", n32, b16, 1500, 0, 1, 8, NFFTB200_LINEAR);
