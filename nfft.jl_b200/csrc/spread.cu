@@ -774,6 +774,22 @@ int peer_spread(nfftb200_plan* p, const void* fhat, void* scratch, int t_lo, int
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
     if (p->timing) { cudaEventRecord(p->evk[0], p->stream); cudaEventRecord(p->evk[1], p->stream); }
+    if constexpr (MT <= 3) {          // opt-in register-footprint spreader (same scratch layout, same peer gather)
+        BinGeom bg;
+        using BL = BinLayout<T, MT, 8>;
+        if (p->kernel_mode == 7 && BL::make(geo.bs, bg) && BL::bytes(bg) <= 227 * 1024) {
+            auto kb = k_spread_bin3d<T, MT, 8>;
+            CUDA_TRY(p, cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BL::bytes(bg)));
+            cudaFuncSetAttribute(kb, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            kb<<<dim3(item_hi - item_lo, 1), NFFTB_BIN_WARPS * 32, BL::bytes(bg), p->stream>>>((const C*)fhat, (C*)scratch, (const T*)p->d_xs,
+                                                                                             p->d_perm, p->d_items, item_lo, p->M, geo,
+                                                                                             make_win<T>(p), make_poly_param<T, MT>(p), bg);
+            if (p->timing) { cudaEventRecord(p->evk[2], p->stream); p->pending_k |= 1; }
+            p->launches++;
+            CUDA_TRY(p, cudaGetLastError());
+            return NFFTB200_OK;
+        }
+    }
     auto kern = k_spread_sub3d<T, MT, true, 8>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(item_hi - item_lo, 1), 256, smem, p->stream>>>((const C*)fhat, nullptr, (C*)scratch, (const T*)p->d_xs, p->d_perm,
