@@ -19,7 +19,7 @@
 //     Horner of tile3d.cuh.
 // FFMA work grows by W^3/(2m)^3 (2.4x for m = 3), shared-memory traffic per node falls from 2*(2m)^3 cells to
 // 2*W^3/(nodes per bin) plus 5 broadcast loads ("per bin" meaning per staged chunk: a chunk is a run of the tile's
-// nodes in the plan's order, so it is spread over all bins of the tile).  One padded tile instead of 8 private sub-tiles: 107 KB for
+// nodes in the plan's order, so it is spread over all bins of the tile).  One padded tile instead of 8 private sub-tiles: 109 KB for
 // Float32, two CTAs per SM.
 //
 // The file holds device code only and is also compiled for the HOST by tests/emu (one OS thread per CUDA thread),
