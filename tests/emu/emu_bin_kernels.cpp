@@ -230,6 +230,12 @@ int main()
     bad += run_case<float, 4, 10>("f32 m=4 (W=10) 32^3", n32, b16, 2000, 100, 1, 5);
     bad += run_case<double, 4, 10>("f64 m=4 (W=10) 32^3", n32, b16, 1200, 0, 1, 6);
     bad += run_case<float, 3, 8>("f32 m=3 thin tiles 16x16x8", nthin, bthin, 1500, 0, 1, 7);
+    // chunk-boundary cases: tile 0 holds exactly one chunk (640 nodes), one chunk + 1, and two split items around 640
+    bad += run_case<float, 3, 8>("f32 m=3 tile 0 with exactly 640 nodes", n32, b16, 660, 639, 1, 12);
+    bad += run_case<float, 3, 8>("f32 m=3 tile 0 with 641 nodes", n32, b16, 661, 640, 1, 13);
+    bad += run_case<float, 3, 8>("f32 m=3 tile 0 with 1282 nodes (items of 642 + 640)", n32, b16, 1300, 1281, 1, 14);
+    bad += run_case<double, 3, 8>("f64 m=3 tile 0 with 513 nodes (chunk 512 + 1)", n32, b16, 530, 512, 1, 15);
+    bad += run_case<float, 3, 8>("f32 m=3 seven nodes", n32, b16, 7, 0, 1, 16);
     const int nodd[3] = {24, 30, 28}, bodd[3] = {12, 10, 14};
     bad += run_case<float, 3, 8>("f32 m=3 tiles 12x10x14 (not a multiple of the bin period)", nodd, bodd, 2500, 200, 1, 11);
     const int nwide[3] = {64, 32, 32}, bwide[3] = {32, 16, 16};
