@@ -152,7 +152,7 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
  *   7 = 3-D complex transforms, m <= 4: the opt-in register-footprint kernels (csrc/spread_bin.cuh,
  *       csrc/interp_bin.cuh) -- the nodes of a tile are counting-sorted into bins inside the CTA and the footprints
  *       of a bin are summed in registers; falls back to mode 0 where they do not apply (node-sharded plans use the
- *       spreader for the peer scratch, the slab-direct interpolation stays the default kernel).  Experimental: verified by
+ *       spreader for the peer scratch and the slab-direct form of the interpolator).  Experimental: verified by
  *       host emulation of the kernel sources (tests/emu), hardware run pending. */
 int nfftb200_set_kernel_mode(nfftb200_plan* p, int mode);
 /* number of kernels + library calls this plan has launched so far */

@@ -364,6 +364,23 @@ int peer_interp(nfftb200_plan* p, const SlabTab& st, void* fhat, int t_lo, int t
     if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
+    if constexpr (MT <= 3) {          // opt-in register-window interpolator, slab-direct form
+        BinGeom bg;
+        using IL = InterpBinLayout<T, MT, 8>;
+        if (p->kernel_mode == 7 && IL::make(geo.bs, bg) && IL::bytes(bg) <= 227 * 1024) {
+            auto kb = k_interp_bin3d<T, MT, 8, true>;
+            CUDA_TRY(p, cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IL::bytes(bg)));
+            cudaFuncSetAttribute(kb, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (p->timing) cudaEventRecord(p->evk[3], p->stream);
+            kb<<<dim3(item_hi - item_lo, 1), NFFTB_BIN_WARPS * 32, IL::bytes(bg), p->stream>>>(nullptr, (C*)fhat, (const T*)p->d_xs, p->d_perm,
+                                                                                             p->d_items, item_lo, p->M, geo, make_win<T>(p),
+                                                                                             make_poly_param<T, MT>(p), bg, st);
+            if (p->timing) { cudaEventRecord(p->evk[4], p->stream); p->pending_k |= 2; }
+            p->launches++;
+            CUDA_TRY(p, cudaGetLastError());
+            return NFFTB200_OK;
+        }
+    }
     auto kern = k_interp_row3d<T, MT, true>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUtensorMap tmap;
@@ -421,7 +438,7 @@ int launch_bin3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, i
     if (item_hi == item_lo) return NFFTB200_OK;
     kern<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm,
                                                                                p->d_items, item_lo, p->M, geo, make_win<T>(p),
-                                                                               make_poly_param<T, MT>(p), bg);
+                                                                               make_poly_param<T, MT>(p), bg, SlabTab{});
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;

@@ -60,12 +60,14 @@ template <typename T, int K> __device__ __forceinline__ T bin_halving_reduce(T (
     return v[0];
 }
 
-template <typename T, int MT, int W>
+// PEER = true is the node-sharded form (comm.cu): the grid is never assembled, every z plane of the tile is staged
+// from the slab of the rank that holds it (own memory or a CUDA-IPC mapping read over NVLink), like k_interp_row3d.
+template <typename T, int MT, int W, bool PEER = false>
 __global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, (sizeof(T) == 4 && W <= 8) ? 2 : 1)
 k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::type* __restrict__ fhat,
                const T* __restrict__ xs, const int32_t* __restrict__ perm, const int32_t* __restrict__ items,
                int item_lo, long long M, GeomDev geo, WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp,
-               BinGeom bg)
+               BinGeom bg, const __grid_constant__ SlabTab slabs)
 {
     using C = typename Cplx<T>::type;
     using IL = InterpBinLayout<T, MT, W>;
@@ -97,7 +99,7 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
     const int PXp = bg.PXp, PL = bg.PL, nkeys = bg.ikeys, turns = bg.ikeys / NWARP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    g += (long long)blockIdx.y * geo.gsz;
+    if (!PEER) g += (long long)blockIdx.y * geo.gsz;
     fhat += (long long)blockIdx.y * M;
     T* myrec = rec + warp * RND * RW;
     T* myres = res + warp * 2 * RND;
@@ -113,9 +115,16 @@ k_interp_bin3d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
         const int xg0 = wrapc(x0 + lane, geo.Nt[0], fw), xg1 = wrapc(x0 + lane + 32, geo.Nt[0], fw);
         const bool on0 = lane < PX, on1 = lane + 32 < PX;
         for (int z = 0; z < PZ; z++) {
-            const unsigned gz = (unsigned)wrapc(z0 + z, geo.Nt[2], fw) * geo.Nt[1];
+            unsigned gz = (unsigned)wrapc(z0 + z, geo.Nt[2], fw);
+            const C* gb = g;
+            if (PEER) {                                                     // plane gz lives on rank gz / planes
+                const unsigned owner = gz / (unsigned)slabs.planes;
+                gb = (const C*)slabs.base[owner];
+                gz -= owner * (unsigned)slabs.planes;
+            }
+            gz *= geo.Nt[1];
             for (int y = warp; y < PY; y += NWARP) {
-                const C* src = g + (size_t)(gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
+                const C* src = gb + (size_t)(gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
                 C* dst = P + (z * PL + y * PXp + lane);
                 if (on0) bin_copy_cell_async(dst, src + xg0);
                 if (on1) bin_copy_cell_async(dst + 32, src + xg1);

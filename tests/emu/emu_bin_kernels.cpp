@@ -154,10 +154,29 @@ static int run_case(const char* name, const int Nt[3], const int bs[3], int M, i
             fo[rep].assign((size_t)B * M, C{(T)777, (T)777});
             C* dst = fo[rep].data();
             emu::launch(emu::Dim3{(unsigned)nitems, (unsigned)B, 1}, NFFTB_BIN_WARPS * 32, [&] {
-                k_interp_bin3d<T, MT, W>(grid.data(), dst, xs.data(), perm.data(), items.data(), 0, (long long)M, geo, win, pp, ig);
+                k_interp_bin3d<T, MT, W>(grid.data(), dst, xs.data(), perm.data(), items.data(), 0, (long long)M, geo, win, pp, ig, SlabTab{});
             });
         }
         ideterm = std::memcmp(fo[0].data(), fo[1].data(), sizeof(C) * fo[0].size()) == 0;
+        // node-sharded form: the first grid cut into z-slabs that live in separate allocations ("ranks"); must
+        // reproduce the single-grid result of transform 0 bit for bit
+        {
+            const int nr = Nt[2] % 4 == 0 ? 4 : 2;
+            SlabTab st{};
+            st.n = nr; st.planes = Nt[2] / nr;
+            const size_t slab_cells = (size_t)st.planes * Nt[1] * Nt[0];
+            std::vector<std::vector<C>> slab(nr);
+            for (int r = 0; r < nr; r++) {
+                slab[r].assign(grid.begin() + r * slab_cells, grid.begin() + (r + 1) * slab_cells);
+                st.base[r] = slab[r].data();
+            }
+            std::vector<C> fp((size_t)M, C{(T)777, (T)777});
+            C* dst = fp.data();
+            emu::launch(emu::Dim3{(unsigned)nitems, 1, 1}, NFFTB_BIN_WARPS * 32, [&] {
+                k_interp_bin3d<T, MT, W, true>(nullptr, dst, xs.data(), perm.data(), items.data(), 0, (long long)M, geo, win, pp, ig, st);
+            });
+            if (std::memcmp(fp.data(), fo[0].data(), sizeof(C) * (size_t)M) != 0) { printf("%s: slab-direct interpolation differs\n", name); ideterm = false; }
+        }
         for (int b = 0; b < B; b++)
             for (int i = 0; i < M; i++) {
                 T w[3][L];
