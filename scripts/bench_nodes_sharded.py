@@ -10,7 +10,7 @@ from oracle import nfft_oracle as O
 CFG = {"C4s": ((2 ** 21,), 2 ** 24, 4, np.float64), "C5s": ((256, 256, 256), 2 ** 25, 3, np.float32),
        "C2": ((128, 128, 128), 2 ** 21, 3, np.float32)}
 name = sys.argv[1] if len(sys.argv) > 1 else "C5s"
-kmode = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 6 = NCCL reduce-scatter baseline instead of the fused peer gather
+kmode = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 6 = NCCL reduce-scatter baseline instead of the fused peer gather; 7 = register-footprint kernels on the fused paths
 N, M, m, T = CFG[name]
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)

@@ -22,3 +22,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(spread|interp)_bin3d' -c 2 \
   -o gpurun_out/mode7 -f python scripts/prof_c2.py C2 1 7 >> gpurun_out/first_call.log 2>&1
 tail -40 gpurun_out/first_call.log
+# follow-up on two GPUs (separate call, gpurun --gpus 2): node sharding with the mode-7 kernels on the fused peer paths
+#   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/bench_nodes_sharded.py C5s 7
