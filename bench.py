@@ -21,6 +21,15 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  pocketfft (scipy.fft) sizes its worker pool from that variable when
+# it is first imported, which made the reference arm's two FFTs 5x slower under torchrun than standalone (round-1
+# verdict: 181 -> 509 ms/step).  The reference arm is meant to use every host core, so undo it before numpy/scipy load.
+if "reference" in sys.argv:
+    try:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+    except Exception:
+        os.environ.pop("OMP_NUM_THREADS", None)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -321,11 +321,13 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
     // initParams, src/precomputation.jl:14-29
     static const int m2K[9] = {1, 3, 7, 9, 14, 17, 20, 23, 24};
     p->lut_size = ((int64_t)1 << m2K[std::min(m + 1, 9) - 1]) * m;
-    const double sig_T = dtype == NFFTB200_F32 ? (double)(float)sigma : sigma;
+    // params.σ*N[d] is evaluated in T: σ::Float32 times an Int is a Float32 product (src/precomputation.jl:25-27), so
+    // for non-dyadic σ the Float32 plan's Ñ can differ from the Float64 one (σ=1.1f, N=10: 10 vs 12)
     for (int d = 0; d < D; d++) {
         if (N[d] < 1) { delete p; return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "N[d] must be >= 1"); }
         p->N[d] = N[d];
-        p->Nt[d] = ((int64_t)std::ceil(sig_T * (double)N[d]) / 2) * 2;
+        const double prod = dtype == NFFTB200_F32 ? (double)((float)sigma * (float)N[d]) : sigma * (double)N[d];
+        p->Nt[d] = ((int64_t)std::ceil(prod) / 2) * 2;
         if (p->Nt[d] > (1 << 30)) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "grid dimension too large"); }
     }
     if (dtype == NFFTB200_F32) {

@@ -106,7 +106,8 @@ def init_params(N, T=np.float64, m=None, sigma=None, reltol=None, precompute=POL
     LUTSize = (2 ** K) * m
     # params.sigma is stored as T before it is used (NFFTParams{T,D}.sigma::T)
     sig_T = T(sigma)
-    Nt = tuple((int(np.ceil(float(sig_T) * n)) // 2) * 2 for n in N)
+    # the product sigma*N[d] is a T product (Float32 * Int -> Float32 in Julia), src/precomputation.jl:25-27
+    Nt = tuple((int(np.ceil(float(sig_T * T(n)))) // 2) * 2 for n in N)
     sig_eff = T(Nt[0] / N[0])
     if blockSize is None:
         blockSize = tuple(default_block_size(Nt, d) for d in range(len(N)))

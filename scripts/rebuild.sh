@@ -1,0 +1,14 @@
+#!/bin/bash
+# Incremental build of libnfftb200.so: recompile only the named sources (e.g. `scripts/rebuild.sh spread interp`), relink.
+set -e
+HERE="$(cd "$(dirname "$0")/../nfft.jl_b200/csrc" && pwd)"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-I/usr/include -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ -Wno-deprecated-gpu-targets ${NFFTB_EXTRA_FLAGS}"
+pids=()
+for n in "$@"; do
+  if [ "$n" = tables ]; then ( $NVCC $FLAGS -x cu -c "$HERE/tables.cpp" -o "$HERE/_obj/tables.o" ) & else ( $NVCC $FLAGS -c "$HERE/$n.cu" -o "$HERE/_obj/$n.o" ) & fi
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -Wno-deprecated-gpu-targets -shared -o "$HERE/../libnfftb200.so" "$HERE"/_obj/*.o -lcufft -lcudart -ldl -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+echo "relinked"

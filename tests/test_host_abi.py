@@ -82,6 +82,34 @@ def test_geometry_matches_init_params(nb, N, T, m, sigma):
     L.nfftb200_destroy(h)
 
 
+def test_oversampled_size_uses_the_plan_precision(nb):
+    """Ñ_d = (ceil(Int, σ*N_d) ÷ 2)*2 with σ::T (src/precomputation.jl:25-27): Float32 * Int is a Float32 product, so a
+    Float32 plan with non-dyadic σ can get a different Ñ than the Float64 plan.  Pinned independently of the oracle by
+    the literal formula in numpy scalars; σ=1.1, N=10 is the known case (Ñ = 10 in both precisions, whereas the product
+    Float64(Float32(1.1)) * 10 = 11.0000002 that round 1 used gives 12)."""
+    L = nb.lib()
+
+    def lib_Nt(N, T, sigma):
+        st, h = host_plan(nb, (N,), T, 3, sigma)
+        assert st == 0
+        Nt = (C.c_int64 * 1)()
+        L.nfftb200_get_info(h, Nt, None, None, None, None, None)
+        L.nfftb200_destroy(h)
+        return Nt[0]
+
+    assert lib_Nt(10, np.float32, 1.1) == 10 and lib_Nt(10, np.float64, 1.1) == 10
+    assert O.init_params((10,), np.float32, 3, 1.1).Nt == (10,) and O.init_params((10,), np.float64, 3, 1.1).Nt == (10,)
+    assert (int(np.ceil(float(np.float32(1.1)) * 10)) // 2) * 2 == 12
+    nmis = 0
+    for sigma in (1.1, 1.3, 1.2, 1.7, 1.9, 2.0, 1.25, 1.5):
+        for N in list(range(1, 200)) + [255, 256, 500, 1000, 1023, 2047, 2048]:
+            for T in (np.float32, np.float64):
+                want = (int(np.ceil(T(sigma) * T(N))) // 2) * 2
+                assert lib_Nt(N, T, sigma) == want == O.init_params((N,), T, 3, sigma).Nt[0], (sigma, N, T)
+            nmis += lib_Nt(N, np.float32, sigma) != (int(np.ceil(float(np.float32(sigma)) * N)) // 2) * 2
+    assert nmis > 0          # the double-precision product (the round-1 formula) disagrees somewhere in this sweep
+
+
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("m", [2, 3, 4, 5, 6, 8])
 def test_tables_match_oracle(nb, T, m):
