@@ -127,6 +127,15 @@ struct nfftb200_plan {
     int64_t nitems = 0, cap_items = 0;
     int64_t cap_nodes = 0;
     int max_neigh_1d = 0;            // 1-D: max nodes a tile's output-stationary spreader must bucket
+    // second, finer plan-time order used by the register-window kernels of kernel_mode 8 (spread_lean.cuh /
+    // interp_lean.cuh): inside every tile the nodes are grouped by (owning warp = octant of bins, colour = bin within
+    // the octant); the reported permutation (d_perm, the bit-exact contract) is untouched.  Built lazily (sort.cu).
+    void* d_xs2 = nullptr;           // shifted nodes in (tile, bin) order, D x M
+    int32_t* d_perm2 = nullptr;      // (tile, bin)-sorted position -> caller's node id
+    int32_t* d_bin_start = nullptr;  // ntiles * NQ + 1 absolute start positions
+    bool have_bins = false;
+    int bins_nq = 0;                 // NQ = 8 * S^3 bins per tile the table was built for
+    int64_t cap_bins_nodes = 0, cap_bin_tab = 0;
 
     // sort scratch
     uint32_t* d_keys[2] = {nullptr, nullptr};
@@ -244,6 +253,7 @@ template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
 // stage launchers implemented in the .cu files
 // ---------------------------------------------------------------------------------------
 int nfftb_sort_nodes(nfftb200_plan* p, const void* d_k);                       // sort.cu
+int nfftb_ensure_bins(nfftb200_plan* p, int W, int G);                          // sort.cu: (tile, bin) order for kernel_mode 8
 int nfftb_deconvolve(nfftb200_plan* p, const void* d_f, void* d_g, int B);      // deconv.cu
 int nfftb_deconvolve_transpose(nfftb200_plan* p, const void* d_g, void* d_f, int B);
 // t_lo/t_hi: half-open range of reference tiles ("blocks") whose nodes are processed

@@ -1,0 +1,179 @@
+// interp_lean.cuh -- K4, kernel_mode 8: register-window forward interpolation over the plan-time (tile, bin) order.
+//   replaces toBlock!/calcOneBlock!/calcOneNode! (/root/reference/src/convolution.jl:229-344).
+//
+// Same arithmetic as interp_bin.cuh (kernel_mode 7): the W^3 window of a bin lives in registers (lane r owns the x-rows
+// (y, z) = (r % W, r / W + 4p)), a node is a register dot product with its window-aligned weights, 8 nodes are folded
+// by one halving butterfly.  What changed after the first B200 measurement of mode 7 (profiles/r02_mode7_*):
+//   * the nodes arrive already grouped by (warp = octant of bins, bin) from the plan (sort.cu: k_bin_order), so the
+//     per-chunk staging, key computation, counting sort and the `order` indirection are gone -- a warp reads its
+//     contiguous node list straight from global memory, one round of 8 nodes ahead of the one it is working on;
+//   * denser data now fills the bins (C5: 19 nodes per bin instead of 3 per chunk), so the window load amortises;
+//   * window origins are clamped into the padded tile, so no load is bounds-checked.
+// Float32 only (packed FFMA2 arithmetic); other types keep the default kernels.
+#pragma once
+#include "bin_common.cuh"
+#include "interp_bin.cuh"
+
+template <int MT, int W> struct LeanGeom {
+    static constexpr int L = 2 * MT;
+    static constexpr int G = W - L + 1;
+    static constexpr int S = (W + G - 1) / G;
+    static constexpr int S3 = S * S * S;
+    static constexpr int NQ = 8 * S3;                        // bins per tile: 8 octants x S^3 colours
+    static_assert(W == 8, "lane = (y, z) row mapping below assumes W = 8 (two passes of 32 rows)");
+};
+
+template <int MT, int W> struct LeanInterpLayout {
+    static constexpr int RW = 4 * W;                         // record: wx[W] | wy[W] | wz[W] | window origin (3 ints), pad
+    static bool make(const int* bs, BinGeom& bg) { return bin_make_geom<float, MT, W>(bs, bg); }
+    static size_t bytes(const BinGeom& bg)
+    {
+        return sizeof(float2) * (size_t)bg.PNs + sizeof(float) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW +
+               sizeof(float) * NFFTB_BIN_WARPS * 2 * NFFTB_BIN_ROUND + 16;
+    }
+};
+
+template <int MT, int W, bool PEER>
+__global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, 2)
+k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const float* __restrict__ xs2,
+              const int32_t* __restrict__ perm2, const int32_t* __restrict__ bin_start, const int32_t* __restrict__ items,
+              int item_lo, long long M, GeomDev geo, WinDev<float> win, const __grid_constant__ PolyParam<float, MT> pp,
+              BinGeom bg, const __grid_constant__ SlabTab slabs)
+{
+    using T = float;
+    using C = float2;
+    using LG = LeanGeom<MT, W>;
+    constexpr int L = LG::L, G = LG::G, S3 = LG::S3, NQ = LG::NQ, RW = LeanInterpLayout<MT, W>::RW;
+    constexpr int NWARP = NFFTB_BIN_WARPS, RND = NFFTB_BIN_ROUND, NP = 2;
+    static_assert(RND == 8, "rounds of 8 nodes");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* P = reinterpret_cast<C*>(smem_raw);                                          // [PZ][PL] padded tile
+    T* rec = reinterpret_cast<T*>(P + bg.PNs);                                      // [NWARP][RND][RW]
+    T* res = rec + NWARP * RND * RW;                                                // [NWARP][2 * RND]
+
+    const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
+    const int tile_id = item[0];
+    const int n_lo = item[1], n_hi = item[2];
+    if (n_hi <= n_lo) return;
+    const int tx = tile_id % geo.nb[0];
+    const int ty = (tile_id / geo.nb[0]) % geo.nb[1];
+    const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
+    const int cx0 = tx * geo.bs[0], cy0 = ty * geo.bs[1], cz0 = tz * geo.bs[2];     // first core cell
+    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
+    const int PXp = bg.PXp, PL = bg.PL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!PEER) g += (long long)blockIdx.y * geo.gsz;
+    fhat += (long long)blockIdx.y * M;
+    T* myrec = rec + warp * RND * RW;
+    T* myres = res + warp * 2 * RND;
+
+    // ---- toBlock!: the padded tile (periodic wrap per row), asynchronously
+    {
+        const int x0 = cx0 - MT, y0 = cy0 - MT, z0 = cz0 - MT;
+        const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
+        const int xg0 = wrapc(x0 + lane, geo.Nt[0], fw), xg1 = wrapc(x0 + lane + 32, geo.Nt[0], fw);
+        const bool on0 = lane < PX, on1 = lane + 32 < PX;
+        for (int z = 0; z < PZ; z++) {
+            unsigned gz = (unsigned)wrapc(z0 + z, geo.Nt[2], fw);
+            const C* gb = g;
+            if (PEER) {                                                     // plane gz lives on rank gz / planes
+                const unsigned owner = gz / (unsigned)slabs.planes;
+                gb = (const C*)slabs.base[owner];
+                gz -= owner * (unsigned)slabs.planes;
+            }
+            gz *= geo.Nt[1];
+            for (int y = warp; y < PY; y += NWARP) {
+                const C* src = gb + (size_t)(gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
+                C* dst = P + (z * PL + y * PXp + lane);
+                if (on0) cp_async_cell(dst, src + xg0);
+                if (on1) cp_async_cell(dst + 32, src + xg1);
+            }
+        }
+    }
+
+    // this warp's node list: the S^3 bins of octant `warp`, contiguous in the (tile, bin) order
+    const int q0 = tile_id * NQ + warp * S3;
+    const int nl0 = min(max(bin_start[q0], n_lo), n_hi), nl1 = min(max(bin_start[q0 + S3], n_lo), n_hi);
+    const int rowy = lane & (W - 1), rowz = lane >> 3;                       // row (y, z + 4p) of the window
+    const int wn = lane / 3, wd = lane - 3 * wn;                             // lane = (node of the round, dimension)
+    const int wNt = wd == 0 ? geo.Nt[0] : (wd == 1 ? geo.Nt[1] : geo.Nt[2]);
+    const int wc0 = wd == 0 ? cx0 : (wd == 1 ? cy0 : cz0);
+    const int wmax = (wd == 0 ? PX : (wd == 1 ? PY : PZ)) - W;               // largest window origin inside the tile
+    T xnext = (T)0;
+    if (wn < RND && nl0 + wn < nl1) xnext = xs2[(long long)(nl0 + wn) * 3 + wd];
+    int jnext = (nl0 + lane < nl1 && lane < RND) ? perm2[nl0 + lane] : 0;
+
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                                         // tile resident
+
+    BinRow<T, W> win_row[NP];
+    int c0 = -1, c1 = -1, c2 = -1;                                           // origin of the resident window
+    for (int rbase = nl0; rbase < nl1; rbase += RND) {
+        const int nn = min(RND, nl1 - rbase);
+        const T x = xnext;
+        const int jdst = jnext;
+        {   // next round's coordinates and destinations: in flight while this round is worked on
+            const int nb0 = rbase + RND;
+            if (wn < RND && nb0 + wn < nl1) xnext = xs2[(long long)(nb0 + wn) * 3 + wd];
+            if (lane < RND && nb0 + lane < nl1) jnext = perm2[nb0 + lane];
+        }
+        if (wn < nn) {                                                       // weights of (node wn of the round, dimension wd)
+            T ks;
+            const int c = node_cell<T>(x, wNt, ks);
+            T w[L];
+            eval_taps<T, MT>(win, pp, ks, c, w);
+            const int lc = c - wc0;                                          // first tap at padded coordinate lc + 1
+            const int wo = min(1 + bin_first<W, G>(bin_of<W, G>(lc)), wmax);
+            const int dl = lc + 1 - wo;                                      // first tap inside the window
+            reinterpret_cast<int*>(myrec + wn * RW + 3 * W)[wd] = wo;
+            T* rn = myrec + wn * RW + wd * W;                                // 2m taps at [dl, dl + 2m), zeros elsewhere
+#pragma unroll
+            for (int l = 0; l < L; l++) rn[dl + l] = w[l];
+#pragma unroll
+            for (int j = 0; j < W - L; j++) rn[j < dl ? j : j + L] = (T)0;
+        }
+        __syncwarp();
+        T v[2 * RND];
+#pragma unroll
+        for (int n = 0; n < RND; n++) {
+            C sn = make_float2(0.f, 0.f);
+            if (n < nn) {                                                    // warp-uniform
+                const T* rn = myrec + n * RW;
+                const int4 org = *reinterpret_cast<const int4*>(rn + 3 * W);
+                if (org.x != c0 || org.y != c1 || org.z != c2) {             // warp-uniform: first node of a bin
+                    c0 = org.x; c1 = org.y; c2 = org.z;
+                    const C* row = P + ((c2 + rowz) * PL + (c1 + rowy) * PXp + c0);
+#pragma unroll
+                    for (int p = 0; p < NP; p++) {
+#pragma unroll
+                        for (int k = 0; k < W; k++) win_row[p].set(k, row[p * 4 * PL + k]);
+                    }
+                }
+                T wx[W];
+                bin_load_row<T, W>(rn, wx);
+                const T wy = rn[W + rowy];
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const T wyz = wy * rn[2 * W + rowz + 4 * p];
+                    win_row[p].dot_acc(wx, wyz, sn);
+                }
+            }
+            v[2 * n] = sn.x; v[2 * n + 1] = sn.y;
+        }
+        int idx;
+        if (nn > RND / 2) {
+            const T tot = bin_halving_reduce<T, 2 * RND>(v, lane, idx);
+            if ((lane & (32 / (2 * RND) - 1)) == 0) myres[idx] = tot;
+        } else {
+            T h[RND];
+#pragma unroll
+            for (int k = 0; k < RND; k++) h[k] = v[k];
+            const T tot = bin_halving_reduce<T, RND>(h, lane, idx);
+            if ((lane & (32 / RND - 1)) == 0) myres[idx] = tot;
+        }
+        __syncwarp();
+        if (lane < nn) fhat[jdst] = make_float2(myres[2 * lane], myres[2 * lane + 1]);
+        __syncwarp();                                                        // records and results free for the next round
+    }
+}

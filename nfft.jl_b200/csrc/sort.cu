@@ -316,7 +316,145 @@ template <typename T> int sort_impl(nfftb200_plan* p, const void* d_k)
     return NFFTB200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// (tile, bin) order for the register-window kernels of kernel_mode 8.  One CTA per tile re-orders the tile's nodes
+// (already contiguous and in ascending caller index after the radix sort) by the bin key
+//     q = octant * S^3 + colour,  octant = sum_d (b_d / S) 2^d,  colour = sum_d (b_d % S) S^d,
+// b_d = bin of the node's first tap along d (bins of G, ..., G, W-(S-1)G first-tap positions per period of W, see
+// bin_of in bin_common.cuh).  Stable (ascending caller index inside a bin) and free of data-dependent atomics: every
+// warp ranks a contiguous part of the tile with __match_any_sync, two passes (count, then place).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BINQ_MAX = 216;      // 8 * 3^3
+
+__device__ __forceinline__ int binq_1d(int lc, int W, int G, int S)
+{
+    const int per = lc / W, r = (lc - per * W) / G;
+    return S * per + (r < S - 1 ? r : S - 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bin_order(const T* __restrict__ xs, const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_start,
+            GeomDev g, int W, int G, int S, int NQ, T* __restrict__ xs2, int32_t* __restrict__ perm2,
+            int32_t* __restrict__ bin_start, long long ntiles)
+{
+    __shared__ int wh[8][BINQ_MAX];
+    __shared__ int tot[BINQ_MAX + 1];
+    const int t = blockIdx.x;
+    const int lo = tile_start[t], hi = tile_start[t + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = t % g.nb[0], ty = (t / g.nb[0]) % g.nb[1], tz = t / (g.nb[0] * g.nb[1]);
+    const int c0[3] = {tx * g.bs[0], ty * g.bs[1], tz * g.bs[2]};
+    for (int i = threadIdx.x; i < 8 * BINQ_MAX; i += 256) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const int n = hi - lo;
+    const int per_warp = ((n + 8 * 32 - 1) / (8 * 32)) * 32;          // whole groups of 32 per warp
+    const int w_lo = lo + warp * per_warp, w_hi = min(hi, w_lo + per_warp);
+    const unsigned lt = (1u << lane) - 1u;
+    auto key_of = [&](int i) {
+        int o = 0, c = 0, sm = 1;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            T ks;
+            const int cell = node_cell<T>(xs[(long long)i * 3 + d], g.Nt[d], ks);
+            const int b = binq_1d(cell - c0[d], W, G, S);
+            const int od = b / S;
+            o += od << d;
+            c += (b - od * S) * sm;
+            sm *= S;
+        }
+        return o * sm + c;
+    };
+    for (int b0 = w_lo; b0 < w_hi; b0 += 32) {                         // pass 1: counts per (warp, bin)
+        const int i = b0 + lane;
+        const bool on = i < w_hi;
+        const int q = on ? key_of(i) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, q);
+        if (on && (peers & lt) == 0) wh[warp][q] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {                                            // exclusive offsets of the warps inside a bin
+        int run = 0;
+        for (int w = 0; w < 8; w++) { const int c = wh[w][threadIdx.x]; wh[w][threadIdx.x] = run; run += c; }
+        tot[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (warp == 0) {                                                   // exclusive scan of the bin totals (<= 216)
+        constexpr int KPL = (BINQ_MAX + 31) / 32;
+        int c[KPL], sum = 0;
+#pragma unroll
+        for (int k = 0; k < KPL; k++) { const int idx = lane * KPL + k; c[k] = idx < NQ ? tot[idx] : 0; sum += c[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < KPL; k++) { const int idx = lane * KPL + k; if (idx < NQ) tot[idx] = run; run += c[k]; }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < NQ; q += 256) bin_start[(long long)t * NQ + q] = lo + tot[q];
+    if (t == ntiles - 1 && threadIdx.x == 0) bin_start[ntiles * NQ] = hi;
+    for (int b0 = w_lo; b0 < w_hi; b0 += 32) {                         // pass 2: place
+        const int i = b0 + lane;
+        const bool on = i < w_hi;
+        const int q = on ? key_of(i) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, q);
+        const int r = __popc(peers & lt);
+        int base = 0;
+        if (on) base = wh[warp][q];
+        __syncwarp();
+        if (on) {
+            const long long pos = (long long)lo + tot[q] + base + r;
+            xs2[pos * 3 + 0] = xs[(long long)i * 3 + 0];
+            xs2[pos * 3 + 1] = xs[(long long)i * 3 + 1];
+            xs2[pos * 3 + 2] = xs[(long long)i * 3 + 2];
+            perm2[pos] = perm[i];
+            if (r == 0) wh[warp][q] = base + __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T> int bins_impl(nfftb200_plan* p, int W, int G)
+{
+    const int S = (W + G - 1) / G, NQ = 8 * S * S * S;
+    if (p->D != 3 || NQ > BINQ_MAX) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "bin order: unsupported geometry");
+    for (int d = 0; d < 3; d++)
+        if (p->bs[d] > 2 * W) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "bin order: tile wider than two bin periods");
+    if (p->have_bins && p->bins_nq == NQ) return NFFTB200_OK;
+    const int64_t M = std::max<int64_t>(p->M, 1);
+    if (M > p->cap_bins_nodes) {
+        if (p->d_xs2) cudaFree(p->d_xs2);
+        if (p->d_perm2) cudaFree(p->d_perm2);
+        p->d_xs2 = nullptr; p->d_perm2 = nullptr; p->cap_bins_nodes = 0;
+        CUDA_TRY(p, cudaMalloc(&p->d_xs2, (size_t)M * 3 * sizeof(T)));
+        CUDA_TRY(p, cudaMalloc((void**)&p->d_perm2, (size_t)M * 4));
+        p->cap_bins_nodes = M;
+    }
+    const int64_t tab = p->ntiles * NQ + 1;
+    if (tab > p->cap_bin_tab) {
+        if (p->d_bin_start) cudaFree(p->d_bin_start);
+        p->d_bin_start = nullptr; p->cap_bin_tab = 0;
+        CUDA_TRY(p, cudaMalloc((void**)&p->d_bin_start, (size_t)tab * 4));
+        p->cap_bin_tab = tab;
+    }
+    k_bin_order<T><<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const T*)p->d_xs, p->d_perm, p->d_tile_start, make_geom<T>(p), W, G, S,
+                                                              NQ, (T*)p->d_xs2, p->d_perm2, p->d_bin_start, p->ntiles);
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    p->have_bins = true;
+    p->bins_nq = NQ;
+    return NFFTB200_OK;
+}
+
 }  // namespace
+
+int nfftb_ensure_bins(nfftb200_plan* p, int W, int G)
+{
+    return p->dtype == NFFTB200_F32 ? bins_impl<float>(p, W, G) : bins_impl<double>(p, W, G);
+}
 
 int nfftb_sort_nodes(nfftb200_plan* p, const void* d_k)
 {

@@ -1,0 +1,209 @@
+// spread_lean.cuh -- K3, kernel_mode 8: register-window adjoint gridding over the plan-time (tile, bin) order.
+//   replaces fillBlock!/fillOneNode! (/root/reference/src/convolution.jl:445-492); hands the same padded tile
+//   ("blocks[l]") to the same gather pass (addBlock!, :371-443) as the other 3-D spreaders.
+//
+// Same arithmetic as spread_bin.cuh (kernel_mode 7): the footprints of a bin's nodes are summed in a W^3 register
+// window (lane r owns the x-rows (y, z) = (r % W, r / W + 4p)) and shared memory sees one read-modify-write per bin.
+// What changed after the first B200 measurement of mode 7 (profiles/r02_mode7_*: 661 us, 158 warp instructions per
+// node, 26 % of the stall samples at the colour barriers):
+//   * the nodes arrive grouped by (warp = octant of bins, colour) from the plan (sort.cu: k_bin_order): no staging,
+//     no in-kernel sort, and dense data fills the bins (C5: 19 nodes per bin instead of 3 per staged chunk);
+//   * the 27 CTA barriers between the colours are replaced by per-warp progress counters: a warp may accumulate the
+//     bin of colour c in registers at once, and only its read-modify-write waits until every other warp has
+//     finished its colours < c.  Still no atomics on the data path and a fixed summation order (bit-reproducible);
+//   * the next round's coordinates and values (a dependent perm -> fHat gather) are fetched one round ahead.
+// Float32 only (packed FFMA2 arithmetic); other types keep the default kernels.
+#pragma once
+#include "bin_common.cuh"
+#include "interp_lean.cuh"
+
+template <int MT, int W> struct LeanSpreadLayout {
+    static constexpr int RW = 4 * W + 4;                     // record: wx[W] | wy[W] | (wz * v)[W] re, im | window origin (3 ints)
+    static bool make(const int* bs, BinGeom& bg) { return bin_make_geom<float, MT, W>(bs, bg); }
+    static size_t bytes(const BinGeom& bg)
+    {
+        return sizeof(float2) * (size_t)bg.PNs + sizeof(float) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW + 64 + 16;
+    }
+};
+
+__device__ __forceinline__ int lean_ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lean_st_release(int* p, int v)
+{
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+template <int MT, int W>
+__global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, 2)
+k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, const float* __restrict__ xs2,
+              const int32_t* __restrict__ perm2, const int32_t* __restrict__ bin_start, const int32_t* __restrict__ items,
+              int item_lo, long long M, GeomDev geo, WinDev<float> win, const __grid_constant__ PolyParam<float, MT> pp,
+              BinGeom bg)
+{
+    using T = float;
+    using C = float2;
+    using LG = LeanGeom<MT, W>;
+    constexpr int L = LG::L, G = LG::G, S3 = LG::S3, NQ = LG::NQ, RW = LeanSpreadLayout<MT, W>::RW;
+    constexpr int NWARP = NFFTB_BIN_WARPS, NTHR = NWARP * 32, RND = NFFTB_BIN_ROUND, NP = 2;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* P = reinterpret_cast<C*>(smem_raw);                                          // [PZ][PL] padded tile
+    T* rec = reinterpret_cast<T*>(P + bg.PNs);                                      // [NWARP][RND][RW]
+    int* done = reinterpret_cast<int*>(rec + NWARP * RND * RW);                     // [NWARP] colours finished per warp
+
+    const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
+    const int tile_id = item[0];
+    const int n_lo = item[1], n_hi = item[2];
+    const int tx = tile_id % geo.nb[0];
+    const int ty = (tile_id / geo.nb[0]) % geo.nb[1];
+    const int tz = tile_id / (geo.nb[0] * geo.nb[1]);
+    const int cx0 = tx * geo.bs[0], cy0 = ty * geo.bs[1], cz0 = tz * geo.bs[2];     // first core cell
+    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L, PZ = geo.bs[2] + L;
+    const int PXp = bg.PXp, PL = bg.PL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    fhat += (long long)blockIdx.y * M;
+    scratch += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)PX * PY * PZ);
+    T* myrec = rec + warp * RND * RW;
+
+    // the S^3 + 1 bin boundaries of this warp's octant: one load per lane, handed out by shuffles
+    const int q0 = tile_id * NQ + warp * S3;
+    static_assert(S3 + 1 <= 32, "one bin boundary per lane");
+    const int bsl = min(max(bin_start[q0 + min(lane, S3)], n_lo), n_hi);
+    const int nl0 = __shfl_sync(0xffffffffu, bsl, 0), nl1 = __shfl_sync(0xffffffffu, bsl, S3);
+    const int rowy = lane & (W - 1), rowz = lane >> 3;                       // row (y, z + 4p) of the window
+    const int wn = lane / 3, wd = lane - 3 * wn;                             // lane = (node of the round, dimension)
+    const int wNt = wd == 0 ? geo.Nt[0] : (wd == 1 ? geo.Nt[1] : geo.Nt[2]);
+    const int wc0 = wd == 0 ? cx0 : (wd == 1 ? cy0 : cz0);
+
+    // first round's inputs in flight while the tile is zeroed
+    T xnext = (T)0;
+    C vnext = make_float2(0.f, 0.f);
+    if (wn < RND && nl0 + wn < nl1) {
+        xnext = xs2[(long long)(nl0 + wn) * 3 + wd];
+        if (wd == 2) vnext = fhat[perm2[nl0 + wn]];
+    }
+    {
+        uint4* z = reinterpret_cast<uint4*>(P);
+        const int n16 = (int)((sizeof(C) * (size_t)bg.PNs) / 16);
+        for (int q = threadIdx.x; q < n16; q += NTHR) z[q] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x < NWARP) done[threadIdx.x] = 0;
+    }
+    __syncthreads();
+
+    int rbase = nl0 - RND;                                                   // list index of the resident round
+    int pos = nl0;                                                           // next node of this warp's list
+    for (int c = 0; c < S3; c++) {
+        const int hi = __shfl_sync(0xffffffffu, bsl, c + 1);
+        if (hi > pos) {                                                      // warp-uniform: bin of colour c is not empty
+            BinRow<T, W> acc[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) acc[p].zero();
+            int o0 = 0, o1 = 0, o2 = 0;                                      // window origin of the bin, padded-tile coordinates
+            const int lo = pos;
+            for (int i = lo; i < hi; i++) {
+                if (i >= rbase + RND) {                                      // warp-uniform: next round of records
+                    __syncwarp();                                            // the previous round has been read
+                    rbase = i;
+                    const T x = xnext;
+                    const C v = vnext;
+                    {
+                        const int nb0 = rbase + RND;
+                        if (wn < RND && nb0 + wn < nl1) {
+                            xnext = xs2[(long long)(nb0 + wn) * 3 + wd];
+                            if (wd == 2) vnext = fhat[perm2[nb0 + wn]];
+                        }
+                    }
+                    if (wn < RND && rbase + wn < nl1) {                      // weights of (node wn of the round, dimension wd)
+                        T ks;
+                        const int cc = node_cell<T>(x, wNt, ks);
+                        T w[L];
+                        eval_taps<T, MT>(win, pp, ks, cc, w);
+                        const int lc = cc - wc0;                             // first tap at padded coordinate lc + 1
+                        const int wo = 1 + bin_first<W, G>(bin_of<W, G>(lc));
+                        const int dl = lc + 1 - wo;                          // first tap inside the window, in [0, G)
+                        T* rn = myrec + wn * RW;
+                        reinterpret_cast<int*>(rn + 4 * W)[wd] = wo;
+                        if (wd < 2) {
+#pragma unroll
+                            for (int l = 0; l < L; l++) rn[wd * W + dl + l] = w[l];
+#pragma unroll
+                            for (int j = 0; j < W - L; j++) rn[wd * W + (j < dl ? j : j + L)] = (T)0;
+                        } else {
+                            C* rz = reinterpret_cast<C*>(rn + 2 * W);
+#pragma unroll
+                            for (int l = 0; l < L; l++) rz[dl + l] = make_float2(w[l] * v.x, w[l] * v.y);
+#pragma unroll
+                            for (int j = 0; j < W - L; j++) rz[j < dl ? j : j + L] = make_float2(0.f, 0.f);
+                        }
+                    }
+                    __syncwarp();
+                }
+                const T* rn = myrec + (i - rbase) * RW;
+                if (i == lo) {
+                    const int4 org = *reinterpret_cast<const int4*>(rn + 4 * W);
+                    o0 = org.x; o1 = org.y; o2 = org.z;
+                }
+                T wx[W];
+                bin_load_row<T, W>(rn, wx);
+                const T wy = rn[W + rowy];
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz + 4 * p];
+                    acc[p].axpy(wx, wy, vz);
+                }
+            }
+            pos = hi;
+            // every other warp must have finished its colours < c before this window is read-modify-written
+            if (c > 0) {
+                for (;;) {
+                    const int d = (lane < NWARP) ? lean_ld_acquire(done + lane) : S3;
+                    if (__all_sync(0xffffffffu, d >= c)) break;
+                }
+            }
+            // one read-modify-write of the window (cells beyond the padded tile carry zero weights only)
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const int Y = o1 + rowy, Z = o2 + rowz + 4 * p;
+                if (Y < PY && Z < PZ) {
+                    C* row = P + (Z * PL + Y * PXp + o0);
+                    if (o0 + W <= PX) {                                      // warp-uniform: all but the last bin of a row
+#pragma unroll
+                        for (int k = 0; k < W; k++) { C cv = row[k]; acc[p].add_to(cv, k); row[k] = cv; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < W; k++)
+                            if (o0 + k < PX) { C cv = row[k]; acc[p].add_to(cv, k); row[k] = cv; }
+                    }
+                }
+            }
+            __threadfence_block();
+        }
+        __syncwarp();
+        if (lane == 0) lean_st_release(done + warp, c + 1);
+    }
+    __syncthreads();
+
+    // ---- flush the padded tile to its scratch slot, dense [PZ][PY][PX] (what the gather pass reads)
+    if ((PX & 1) == 0) {
+        const int hx = PX >> 1;
+        const unsigned inv_hx = fastdiv_inv(hx), inv_py = fastdiv_inv(PY);
+        for (int idx = threadIdx.x; idx < PZ * PY * hx; idx += NTHR) {
+            const int row = (int)fastdiv(idx, inv_hx), u = idx - row * hx;
+            const int z = (int)fastdiv(row, inv_py), y = row - z * PY;
+            const C* src = P + (z * PL + y * PXp + 2 * u);
+            const C a = src[0], b = src[1];
+            *reinterpret_cast<float4*>(scratch + ((size_t)row * PX + 2 * u)) = make_float4(a.x, a.y, b.x, b.y);
+        }
+    } else {
+        const unsigned inv_px = fastdiv_inv(PX), inv_py = fastdiv_inv(PY);
+        for (int idx = threadIdx.x; idx < PZ * PY * PX; idx += NTHR) {
+            const int row = (int)fastdiv(idx, inv_px), x = idx - row * PX;
+            const int z = (int)fastdiv(row, inv_py), y = row - z * PY;
+            scratch[idx] = P[z * PL + y * PXp + x];
+        }
+    }
+}

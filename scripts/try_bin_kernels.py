@@ -19,6 +19,10 @@ from oracle import nfft_oracle as O
 
 TOL = {np.float32: 1e-5, np.float64: 1e-12}
 out_lines = []
+MODES = (7, 8)            # register-window kernels checked against mode 0: 7 = in-kernel bin sort, 8 = plan-time (tile, bin) order
+for _a in sys.argv[1:]:
+    if _a.startswith("--modes="):
+        MODES = tuple(int(x) for x in _a.split("=")[1].split(","))
 
 
 def emit(d):
@@ -50,7 +54,7 @@ def parity_case(name, N, M, T, m, B=1, cluster=0, blockSize=None, oracle=True):
     f = O.random_complex(tuple(N) + ((B,) if B > 1 else ()), T, 6)
     res, fwd = {}, {}
     launches = {}
-    for mode in (0, 7):
+    for mode in (0,) + MODES:
         p.set_kernel_mode(mode)
         l0 = p.launch_count()
         res[mode] = np.array(p.adjoint() * fh)
@@ -59,17 +63,21 @@ def parity_case(name, N, M, T, m, B=1, cluster=0, blockSize=None, oracle=True):
         assert np.array_equal(res[mode], again), f"adjoint, mode {mode}: not bit-reproducible"
         fwd[mode] = np.array(p * f)
         assert np.array_equal(fwd[mode], np.array(p * f)), f"forward, mode {mode}: not bit-reproducible"
-    e = rel(res[7], res[0])
-    ef = rel(fwd[7], fwd[0])
-    d = {"case": name, "N": list(N), "M": M, "dtype": np.dtype(T).name, "m": m, "B": B, "rel_mode7_vs_mode0": e,
-         "fwd_rel_mode7_vs_mode0": ef, "launches": launches}
-    ok = e <= TOL[T] and ef <= TOL[T]
-    if oracle and B == 1:
-        po = O.OraclePlan(k, N, m=m, sigma=2.0, blockSize=p.params.blockSize)
-        ref = po.adjoint(fh)
-        d["rel_mode7_vs_oracle"] = rel(res[7], ref)
-        d["fwd_rel_mode7_vs_oracle"] = rel(fwd[7], po.forward(f))
-        ok = ok and d["rel_mode7_vs_oracle"] <= TOL[T] and d["fwd_rel_mode7_vs_oracle"] <= TOL[T]
+    d = {"case": name, "N": list(N), "M": M, "dtype": np.dtype(T).name, "m": m, "B": B, "launches": launches}
+    ok = True
+    po = O.OraclePlan(k, N, m=m, sigma=2.0, blockSize=p.params.blockSize) if (oracle and B == 1) else None
+    ref_a = po.adjoint(fh) if po else None
+    ref_f = po.forward(f) if po else None
+    for mode in MODES:
+        e = rel(res[mode], res[0])
+        ef = rel(fwd[mode], fwd[0])
+        d[f"rel_mode{mode}_vs_mode0"] = e
+        d[f"fwd_rel_mode{mode}_vs_mode0"] = ef
+        ok = ok and e <= TOL[T] and ef <= TOL[T]
+        if po:
+            d[f"rel_mode{mode}_vs_oracle"] = rel(res[mode], ref_a)
+            d[f"fwd_rel_mode{mode}_vs_oracle"] = rel(fwd[mode], ref_f)
+            ok = ok and d[f"rel_mode{mode}_vs_oracle"] <= TOL[T] and d[f"fwd_rel_mode{mode}_vs_oracle"] <= TOL[T]
     d["ok"] = bool(ok)
     emit(d)
     return ok
@@ -84,7 +92,7 @@ def time_case(name, N, M, T, m):
     fho = p.empty_out()
     ts = nb.TimingStats()
     d = {"case": name, "N": list(N), "M": M, "dtype": np.dtype(T).name, "m": m}
-    for mode in (0, 7):
+    for mode in (0,) + MODES:
         p.set_kernel_mode(mode)
         acc = np.zeros(3); n = 0
         for i in range(13):
