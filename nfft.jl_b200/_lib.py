@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnfftb200.so")
+LIB_PATH = os.environ.get("NFFTB200_LIB") or os.path.join(_HERE, "libnfftb200.so")   # NFFTB200_LIB: another build of the same ABI
 
 # every symbol include/nfftb200.h declares
 SYMBOLS = [

@@ -8,7 +8,7 @@ NCCL_INC=${NCCL_INC:-/usr/include}
 FLAGS="-I$NCCL_INC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ ${NFFTB_EXTRA_FLAGS}"
 mkdir -p "$HERE/_obj"
 pids=()
-for f in plan.cu sort.cu deconv.cu spread.cu interp.cu comm.cu oned.cu twod.cu toeplitz.cu sdc.cu; do
+for f in plan.cu sort.cu deconv.cu spread.cu interp.cu comm.cu oned.cu twod.cu toeplitz.cu sdc.cu lean.cu; do
   ( $NVCC $FLAGS -c "$HERE/$f" -o "$HERE/_obj/${f%.cu}.o" ) &
   pids+=($!)
 done

@@ -253,7 +253,11 @@ template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
 // stage launchers implemented in the .cu files
 // ---------------------------------------------------------------------------------------
 int nfftb_sort_nodes(nfftb200_plan* p, const void* d_k);                       // sort.cu
-int nfftb_ensure_bins(nfftb200_plan* p, int W, int G);                          // sort.cu: (tile, bin) order for kernel_mode 8
+int nfftb_ensure_bins(nfftb200_plan* p, int W, int G);
+// lean.cu (kernel_mode 8, Float32 3-D): -1 when the kernels do not apply; scratch_override / slabs select the node-sharded forms
+int nfftb_spread_lean(nfftb200_plan* p, const void* fhat, void* g, void* scratch_override, int B, int t_lo, int t_hi);
+int nfftb_interp_lean(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi, const SlabTab* slabs);
+int nfftb_gather_scratch(nfftb200_plan* p, const void* scratch, void* g, int B, int t_lo, int t_hi, int item_lo, int item_hi);   // spread.cu                          // sort.cu: (tile, bin) order for kernel_mode 8
 int nfftb_deconvolve(nfftb200_plan* p, const void* d_f, void* d_g, int B);      // deconv.cu
 int nfftb_deconvolve_transpose(nfftb200_plan* p, const void* d_g, void* d_f, int B);
 // t_lo/t_hi: half-open range of reference tiles ("blocks") whose nodes are processed

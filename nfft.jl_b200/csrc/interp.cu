@@ -16,7 +16,6 @@
 #include "window.cuh"
 #include "tile3d.cuh"
 #include "interp_bin.cuh"
-#include "interp_lean.cuh"
 
 namespace {
 
@@ -446,43 +445,6 @@ int launch_bin3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, i
 }
 
 
-// kernel_mode 8: register-window interpolator over the plan-time (tile, bin) order (interp_lean.cuh); Float32 only;
-// -1 when it does not apply.  `st` != nullptr selects the slab-direct (node-sharded) form.
-template <int MT, int W>
-int launch_lean3d(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi, const SlabTab* slabs)
-{
-    using T = float;
-    using C = float2;
-    using ILy = LeanInterpLayout<MT, W>;
-    GeomDev geo = make_geom<T>(p);
-    BinGeom bg;
-    for (int d = 0; d < 3; d++) if (geo.bs[d] > 2 * W || geo.bs[d] + 2 * MT < W) return -1;
-    if (!ILy::make(geo.bs, bg)) return -1;
-    const size_t smem = ILy::bytes(bg);
-    if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64) return -1;
-    if (nfftb_ensure_bins(p, W, LeanGeom<MT, W>::G) != NFFTB200_OK) return -1;
-    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
-    if (item_hi == item_lo) return NFFTB200_OK;
-    if (slabs) {
-        auto kern = k_interp_lean<MT, W, true>;
-        CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        kern<<<dim3(item_hi - item_lo, 1), NFFTB_BIN_WARPS * 32, smem, p->stream>>>(nullptr, (C*)fhat, (const T*)p->d_xs2, p->d_perm2,
-                                                                                   p->d_bin_start, p->d_items, item_lo, p->M, geo,
-                                                                                   make_win<T>(p), make_poly_param<T, MT>(p), bg, *slabs);
-    } else {
-        auto kern = k_interp_lean<MT, W, false>;
-        CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        kern<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs2, p->d_perm2,
-                                                                                   p->d_bin_start, p->d_items, item_lo, p->M, geo,
-                                                                                   make_win<T>(p), make_poly_param<T, MT>(p), bg, SlabTab{});
-    }
-    p->launches++;
-    CUDA_TRY(p, cudaGetLastError());
-    return NFFTB200_OK;
-}
-
 template <typename T>
 int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_complex, int t_lo, int t_hi,
                 long long i_lo, long long i_hi)
@@ -501,16 +463,9 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
         const int r = nfftb_interp_2d(p, g, fhat, B, t_lo, t_hi);
         if (r >= 0) return r;
     }
-    if constexpr (sizeof(T) == 4) {
-        if (nfftb_tiled_ok(p) && is_complex && p->D == 3 && p->kernel_mode == 8) {
-            int r = -1;                                // register-window interpolator over the (tile, bin) order
-            switch (p->m) {
-                case 2: r = launch_lean3d<2, 8>(p, g, fhat, B, t_lo, t_hi, nullptr); break;
-                case 3: r = launch_lean3d<3, 8>(p, g, fhat, B, t_lo, t_hi, nullptr); break;
-                default: break;
-            }
-            if (r >= 0) return r;
-        }
+    if (sizeof(T) == 4 && nfftb_tiled_ok(p) && is_complex && p->D == 3 && p->kernel_mode == 8) {
+        const int r = nfftb_interp_lean(p, g, fhat, B, t_lo, t_hi, nullptr);      // lean.cu: (tile, bin)-ordered register windows
+        if (r >= 0) return r;
     }
     if (nfftb_tiled_ok(p) && is_complex && p->D == 3 && p->kernel_mode == 7) {
         int r = -1;                                    // opt-in register-window interpolator (interp_bin.cuh)

@@ -18,7 +18,6 @@
 #include "window.cuh"
 #include "tile3d.cuh"
 #include "spread_bin.cuh"
-#include "spread_lean.cuh"
 
 namespace {
 
@@ -749,73 +748,6 @@ int launch_bin3d(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, i
 }
 
 
-// kernel_mode 8: register-window spreader over the plan-time (tile, bin) order (spread_lean.cuh) + the same scratch
-// layout and gather pass.  Float32 only.  Returns -1 when it does not apply (the caller runs the default kernel).
-template <int MT, int W>
-int launch_lean3d(nfftb200_plan* p, const void* fhat, void* g, void* scratch_override, int B, int t_lo, int t_hi)
-{
-    using T = float;
-    using C = float2;
-    using SLy = LeanSpreadLayout<MT, W>;
-    GeomDev geo = make_geom<T>(p);
-    BinGeom bg;
-    for (int d = 0; d < 3; d++) if (geo.bs[d] > 2 * W || geo.bs[d] + 2 * MT < W) return -1;
-    if (!SLy::make(geo.bs, bg)) return -1;
-    const size_t smem = SLy::bytes(bg);
-    if (smem > 227 * 1024) return -1;
-    for (int d = 0; d < 3; d++) {
-        const int last = geo.Nt[d] - (geo.nb[d] - 1) * geo.bs[d];
-        if (geo.bs[d] < MT || last < MT) return -1;                   // halos would reach past the neighbour
-        if (d == 0 && ((geo.bs[0] & 1) || (last & 1))) return -1;     // the gather works on x cell pairs
-    }
-    if (nfftb_ensure_bins(p, W, LeanGeom<MT, W>::G) != NFFTB200_OK) return -1;
-    const size_t PN = (size_t)(geo.bs[0] + 2 * MT) * (geo.bs[1] + 2 * MT) * (geo.bs[2] + 2 * MT);
-    const cudaStream_t st = p->stream;
-    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
-    if (item_hi == item_lo) return scratch_override ? NFFTB200_OK : -1;
-    void* scratch = scratch_override;
-    if (!scratch) {
-        const int64_t need = (int64_t)(sizeof(C) * PN * (size_t)(item_hi - item_lo) * B);
-        if (need > p->cap_tilebuf) {
-            if (p->d_tilebuf) cudaFree(p->d_tilebuf);
-            p->d_tilebuf = nullptr; p->cap_tilebuf = 0;
-            if (cudaMalloc(&p->d_tilebuf, (size_t)need) != cudaSuccess) { cudaGetLastError(); return -1; }
-            p->cap_tilebuf = need;
-        }
-        scratch = p->d_tilebuf;
-    }
-    p->have_gather_ev = false;
-    if (p->timing) { cudaEventRecord(p->evk[0], st); cudaEventRecord(p->evk[1], st); }
-    auto kern = k_spread_lean<MT, W>;
-    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, st>>>((const C*)fhat, (C*)scratch, (const T*)p->d_xs2, p->d_perm2,
-                                                                        p->d_bin_start, p->d_items, item_lo, p->M, geo, make_win<T>(p),
-                                                                        make_poly_param<T, MT>(p), bg);
-    p->launches++;
-    if (scratch_override) {                                           // node sharding: the peer gather follows separately
-        if (p->timing) { cudaEventRecord(p->evk[2], st); p->pending_k |= 1; }
-        CUDA_TRY(p, cudaGetLastError());
-        return NFFTB200_OK;
-    }
-    if (p->timing) { cudaEventRecord(p->evk[5], st); p->have_gather_ev = true; }
-    const int units = geo.Nt[0] / 2;
-    int bx = 32;
-    if (geo.bs[2] == 16 && geo.Nt[2] % 16 == 0 && 16 >= 2 * MT) {
-        while (bx < 128 && bx < units) bx <<= 1;
-        dim3 gc((units + bx - 1) / bx, geo.Nt[1], geo.nb[2] * B * 2);
-        k_gather_cols3d<T, MT, 16, false, 2><<<gc, bx, 0, st>>>((const C*)scratch, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo, PeerTab{}, 0);
-    } else {
-        while (bx < 256 && bx < units) bx <<= 1;
-        dim3 gg((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);
-        k_gather_tiles3d<T, MT><<<gg, bx, 0, st>>>((const C*)scratch, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo);
-    }
-    if (p->timing) { cudaEventRecord(p->evk[2], st); p->pending_k |= 1; }
-    p->launches++;
-    CUDA_TRY(p, cudaGetLastError());
-    return NFFTB200_OK;
-}
-
 // ---- node sharding over peer memory (comm.cu): spread the own tile range into an IPC-exported scratch, then
 // gather the own z-slab from every rank's scratch
 template <typename T, int MT>
@@ -916,16 +848,9 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
             return r;
         }
     }
-    if constexpr (sizeof(T) == 4) {
-        if (i_hi > i_lo && nfftb_tiled_ok(p) && is_complex && p->D == 3 && p->kernel_mode == 8) {
-            int r = -1;                                // register-window spreader over the (tile, bin) order (spread_lean.cuh)
-            switch (p->m) {
-                case 2: r = launch_lean3d<2, 8>(p, fhat, g, nullptr, B, t_lo, t_hi); break;
-                case 3: r = launch_lean3d<3, 8>(p, fhat, g, nullptr, B, t_lo, t_hi); break;
-                default: break;
-            }
-            if (r >= 0) return r;
-        }
+    if (sizeof(T) == 4 && i_hi > i_lo && nfftb_tiled_ok(p) && is_complex && p->D == 3 && p->kernel_mode == 8) {
+        const int r = nfftb_spread_lean(p, fhat, g, nullptr, B, t_lo, t_hi);    // lean.cu: (tile, bin)-ordered register windows
+        if (r >= 0) return r;
     }
     if (i_hi > i_lo && nfftb_tiled_ok(p) && is_complex && p->D == 3 && p->kernel_mode == 7) {
         int r = -1;                                    // opt-in register-footprint spreader (spread_bin.cuh)
@@ -1017,6 +942,38 @@ int nfftb_peer_gather(nfftb200_plan* p, void* d_slab, int layer_lo, int nlayers,
 {
     PEER_DISPATCH(peer_gather, p, d_slab, layer_lo, nlayers, pt)
     return nfftb_fail(p, NFFTB200_UNSUPPORTED, "peer gather: unsupported m");
+}
+
+// gather pass over a scratch of padded tiles written by any of the 3-D spreaders (used by lean.cu)
+int nfftb_gather_scratch(nfftb200_plan* p, const void* scratch, void* g, int B, int t_lo, int t_hi, int item_lo, int item_hi)
+{
+    if (p->dtype != NFFTB200_F32) return -1;
+    using T = float;
+    using C = float2;
+    GeomDev geo = make_geom<T>(p);
+    const int units = geo.Nt[0] / 2;
+    int bx = 32;
+    const cudaStream_t st = p->stream;
+#define GS_CASE(MT)                                                                                                              \
+    case MT:                                                                                                                     \
+        if (geo.bs[2] == 16 && geo.Nt[2] % 16 == 0 && 16 >= 2 * MT) {                                                            \
+            while (bx < 128 && bx < units) bx <<= 1;                                                                             \
+            dim3 gc((units + bx - 1) / bx, geo.Nt[1], geo.nb[2] * B * 2);                                                        \
+            k_gather_cols3d<T, MT, 16, false, 2><<<gc, bx, 0, st>>>((const C*)scratch, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo, PeerTab{}, 0); \
+        } else {                                                                                                                 \
+            while (bx < 256 && bx < units) bx <<= 1;                                                                             \
+            dim3 gg((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);                                                            \
+            k_gather_tiles3d<T, MT><<<gg, bx, 0, st>>>((const C*)scratch, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo); \
+        }                                                                                                                        \
+        break;
+    switch (p->m) {
+        GS_CASE(2) GS_CASE(3)
+        default: return -1;
+    }
+#undef GS_CASE
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
 }
 
 int nfftb_spread(nfftb200_plan* p, const void* d_fhat, void* d_g, int B, int is_complex, int64_t t_lo,

@@ -7,7 +7,7 @@ FLAGS="-I/usr/include -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -li
 # a change of a header every object sees (the plan struct!) means every object must be rebuilt
 set -- "$@"
 for o in "$HERE"/_obj/*.o; do
-  if [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/../../include/nfftb200.h" -nt "$o" ]; then set -- plan sort deconv spread interp comm oned twod toeplitz sdc tables; break; fi
+  if [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/../../include/nfftb200.h" -nt "$o" ]; then set -- plan sort deconv spread interp comm oned twod toeplitz sdc lean tables; break; fi
 done
 echo "compiling: $*"
 pids=()
