@@ -153,7 +153,12 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
  *       csrc/interp_bin.cuh) -- the nodes of a tile are counting-sorted into bins inside the CTA and the footprints
  *       of a bin are summed in registers; falls back to mode 0 where they do not apply (node-sharded plans use the
  *       spreader for the peer scratch and the slab-direct form of the interpolator).  Experimental: verified by
- *       host emulation of the kernel sources (tests/emu), hardware run pending. */
+ *       host emulation of the kernel sources (tests/emu); measured on B200 in round 2 (661 / 491 us on C2).
+ *   8 = force the (tile, bin)-ordered register-window kernels (csrc/spread_lean.cuh, csrc/interp_lean.cuh): Float32,
+ *       3-D, m = 2 or 3, tiles of at most 16 cells.  Mode 0 already selects them where they apply.
+ *   9 = the round-1 default: warp-private sub-tile spreader / row-per-lane interpolator for every 3-D plan.
+ *  11 = mode 8 with the gather pass fused into the spreader ("last arriver gathers", csrc/spread_lean.cuh); measured
+ *       slower than spread + separate gather on B200, kept as an experiment. */
 int nfftb200_set_kernel_mode(nfftb200_plan* p, int mode);
 /* number of kernels + library calls this plan has launched so far */
 int nfftb200_get_launch_count(nfftb200_plan* p, int64_t* n);

@@ -136,6 +136,12 @@ struct nfftb200_plan {
     bool have_bins = false;
     int bins_nq = 0;                 // NQ = 8 * S^3 bins per tile the table was built for
     int64_t cap_bins_nodes = 0, cap_bin_tab = 0;
+    // fused spread + gather (lean.cu): work items expected at every output block (the items of its distinct neighbour
+    // tiles) and the per-exec arrival counters
+    int32_t* d_expect = nullptr;     // ntiles
+    int32_t* d_ready = nullptr;      // B * ntiles, zeroed before every fused spread
+    std::vector<int32_t> h_expect;
+    int64_t cap_ready = 0;
 
     // sort scratch
     uint32_t* d_keys[2] = {nullptr, nullptr};

@@ -48,13 +48,42 @@ int spread_lean(nfftb200_plan* p, const void* fhat, void* g, void* scratch_overr
         scratch = p->d_tilebuf;
     }
     p->have_gather_ev = false;
+    // fused "last arriver gathers" form (opt-in, kernel_mode 11): the whole grid in one launch, 16-cell-thick tile layers.
+    // Measured on B200 (profiles/r02_fused_gather.txt): C2 1073 us against 528 + 108 us for spread + separate gather, and
+    // MORE DRAM traffic (866 MB vs 834 MB): the scratch tiles a CTA gathers were written 30-70 us earlier by other SMs
+    // but the reads still go to DRAM, and a 256-thread CTA cannot cover that latency.  Kept for the record.
+    const bool fuse = !scratch_override && p->kernel_mode == 11 && t_lo == 0 && t_hi == p->ntiles && geo.bs[2] == 16 &&
+                      geo.Nt[2] % 16 == 0 && 16 >= 2 * MT;
+    if (fuse) {
+        const int64_t need = (int64_t)sizeof(int32_t) * p->ntiles * B;
+        if (need > p->cap_ready) {
+            if (p->d_ready) cudaFree(p->d_ready);
+            p->d_ready = nullptr; p->cap_ready = 0;
+            CUDA_TRY(p, cudaMalloc((void**)&p->d_ready, (size_t)need));
+            p->cap_ready = need;
+        }
+        if (p->timing) { cudaEventRecord(p->evk[0], st); cudaEventRecord(p->evk[1], st); }
+        CUDA_TRY(p, cudaMemsetAsync(p->d_ready, 0, (size_t)need, st));
+        LeanFuse fz{(C*)g, p->d_tile_items, item_hi, (int)p->ntiles, p->d_ready, p->d_expect};
+        auto kf = k_spread_lean<MT, W, true>;
+        CUDA_TRY(p, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        kf<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, st>>>((const C*)fhat, (C*)scratch, (const T*)p->d_xs2, p->d_perm2,
+                                                                          p->d_bin_start, p->d_items, item_lo, p->M, geo, make_win<T>(p),
+                                                                          make_poly_param<T, MT>(p), bg, fz);
+        k_zero_empty_blocks<MT><<<dim3((unsigned)p->ntiles, B), 256, 0, st>>>((C*)g, p->d_expect, geo);
+        p->launches += 3;
+        if (p->timing) { cudaEventRecord(p->evk[2], st); p->pending_k |= 1; }
+        CUDA_TRY(p, cudaGetLastError());
+        return NFFTB200_OK;
+    }
     if (p->timing) { cudaEventRecord(p->evk[0], st); cudaEventRecord(p->evk[1], st); }
-    auto kern = k_spread_lean<MT, W>;
+    auto kern = k_spread_lean<MT, W, false>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<dim3(item_hi - item_lo, B), NFFTB_BIN_WARPS * 32, smem, st>>>((const C*)fhat, (C*)scratch, (const T*)p->d_xs2, p->d_perm2,
                                                                         p->d_bin_start, p->d_items, item_lo, p->M, geo, make_win<T>(p),
-                                                                        make_poly_param<T, MT>(p), bg);
+                                                                        make_poly_param<T, MT>(p), bg, LeanFuse{});
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
     if (scratch_override) {                                           // node sharding: the peer gather follows separately

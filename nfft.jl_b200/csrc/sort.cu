@@ -444,6 +444,29 @@ template <typename T> int bins_impl(nfftb200_plan* p, int W, int G)
                                                               NQ, (T*)p->d_xs2, p->d_perm2, p->d_bin_start, p->ntiles);
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
+    {   // expected arrivals per output block: the work items of its distinct neighbour tiles (periodic)
+        const int64_t nb0 = p->nb[0], nb1 = p->nb[1], nb2 = p->nb[2];
+        p->h_expect.assign((size_t)p->ntiles, 0);
+        auto offs = [](int64_t nb, int (&o)[3]) { int n = 0; if (nb >= 3) { o[n++] = -1; o[n++] = 0; o[n++] = 1; } else if (nb == 2) { o[n++] = -1; o[n++] = 0; } else o[n++] = 0; return n; };
+        int ox[3], oy[3], oz[3];
+        const int nx = offs(nb0, ox), ny = offs(nb1, oy), nz = offs(nb2, oz);
+        for (int64_t tz = 0; tz < nb2; tz++)
+            for (int64_t ty = 0; ty < nb1; ty++)
+                for (int64_t tx = 0; tx < nb0; tx++) {
+                    int32_t e = 0;
+                    for (int c = 0; c < nz; c++)
+                        for (int b = 0; b < ny; b++)
+                            for (int a = 0; a < nx; a++) {
+                                const int64_t t = (((tz + oz[c] + nb2) % nb2) * nb1 + (ty + oy[b] + nb1) % nb1) * nb0 + (tx + ox[a] + nb0) % nb0;
+                                e += p->h_tile_items[(size_t)t + 1] - p->h_tile_items[(size_t)t];
+                            }
+                    p->h_expect[(size_t)((tz * nb1 + ty) * nb0 + tx)] = e;
+                }
+        if (p->d_expect) cudaFree(p->d_expect);
+        p->d_expect = nullptr;
+        CUDA_TRY(p, cudaMalloc((void**)&p->d_expect, sizeof(int32_t) * (size_t)p->ntiles));
+        CUDA_TRY(p, cudaMemcpyAsync(p->d_expect, p->h_expect.data(), sizeof(int32_t) * (size_t)p->ntiles, cudaMemcpyHostToDevice, p->stream));
+    }
     p->have_bins = true;
     p->bins_nq = NQ;
     return NFFTB200_OK;

@@ -16,6 +16,11 @@
 #pragma once
 #include "bin_common.cuh"
 #include "interp_lean.cuh"
+#include "gather3d.cuh"
+
+#ifndef NFFTB_LEAN_EVICT_LAST
+#define NFFTB_LEAN_EVICT_LAST 0     // 1: fused form stores its scratch tile with an L2 evict_last policy
+#endif
 
 template <int MT, int W> struct LeanSpreadLayout {
     static constexpr int RW = 4 * W + 4;                     // record: wx[W] | wy[W] | (wz * v)[W] re, im | window origin (3 ints)
@@ -37,12 +42,27 @@ __device__ __forceinline__ void lean_st_release(int* p, int v)
     asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-template <int MT, int W>
+// what the fused form needs on top: the grid, the item table of the gather and the arrival counters
+struct LeanFuse {
+    float2* g;                   // oversampled grid (all transforms)
+    const int32_t* tile_items;   // ntiles + 1
+    int item_hi;                 // one past the last launched work item
+    int ntiles;
+    int* ready;                  // [B][ntiles] arrivals per output block, zero at launch
+    const int* expect;           // [ntiles] work items among the block's distinct neighbour tiles
+};
+
+// FUSE = true: "last arriver gathers".  After its padded tile is in the scratch, a CTA bumps the arrival counter of the
+// (up to) 27 output blocks its tile overlaps; whoever completes a block's count sums that block right away from the
+// scratch tiles -- written moments ago by neighbouring CTAs, so the reads hit L2 instead of DRAM -- and writes the 16^3
+// grid cells once.  Integer counters only: no floating-point atomics, no waiting (nothing to deadlock on), and the
+// per-cell summation order is the gather pass's fixed order whoever runs it.  Replaces the separate gather launch.
+template <int MT, int W, bool FUSE>
 __global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, 2)
 k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, const float* __restrict__ xs2,
               const int32_t* __restrict__ perm2, const int32_t* __restrict__ bin_start, const int32_t* __restrict__ items,
               int item_lo, long long M, GeomDev geo, WinDev<float> win, const __grid_constant__ PolyParam<float, MT> pp,
-              BinGeom bg)
+              BinGeom bg, const __grid_constant__ LeanFuse fz)
 {
     using T = float;
     using C = float2;
@@ -66,6 +86,7 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
     const int PXp = bg.PXp, PL = bg.PL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     fhat += (long long)blockIdx.y * M;
+    const float2* scratch_base = scratch;
     scratch += ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)PX * PY * PZ);
     T* myrec = rec + warp * RND * RW;
 
@@ -196,6 +217,14 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
             const int z = (int)fastdiv(row, inv_py), y = row - z * PY;
             const C* src = P + (z * PL + y * PXp + 2 * u);
             const C a = src[0], b = src[1];
+#if NFFTB_LEAN_EVICT_LAST
+            if (FUSE) {
+                unsigned long long pol;
+                asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(scratch + ((size_t)row * PX + 2 * u)),
+                             "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "l"(pol) : "memory");
+            } else
+#endif
             *reinterpret_cast<float4*>(scratch + ((size_t)row * PX + 2 * u)) = make_float4(a.x, a.y, b.x, b.y);
         }
     } else {
@@ -205,5 +234,51 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
             const int z = (int)fastdiv(row, inv_py), y = row - z * PY;
             scratch[idx] = P[z * PL + y * PXp + x];
         }
+    }
+    if constexpr (FUSE) {
+        __shared__ int s_glist[27];
+        __shared__ int s_gcount;
+        __threadfence();                                                     // the tile is visible device-wide ...
+        if (threadIdx.x == 0) s_gcount = 0;
+        __syncthreads();                                                     // ... before any arrival is counted
+        const int nb0 = geo.nb[0], nb1 = geo.nb[1], nb2 = geo.nb[2];
+        if (threadIdx.x < 27) {
+            const int ox = (int)threadIdx.x % 3 - 1, oy = ((int)threadIdx.x / 3) % 3 - 1, oz = (int)threadIdx.x / 9 - 1;
+            auto distinct = [](int off, int nb) { return nb >= 3 || (nb == 2 ? off <= 0 : off == 0); };
+            if (distinct(ox, nb0) && distinct(oy, nb1) && distinct(oz, nb2)) {
+                const int nx = (tx + ox + nb0) % nb0, ny = (ty + oy + nb1) % nb1, nz = (tz + oz + nb2) % nb2;
+                const int nbt = (nz * nb1 + ny) * nb0 + nx;
+                const int old = atomicAdd(fz.ready + (size_t)blockIdx.y * fz.ntiles + nbt, 1);
+                if (old + 1 == fz.expect[nbt]) s_glist[atomicAdd(&s_gcount, 1)] = nbt;
+            }
+        }
+        __syncthreads();
+        const int ng = s_gcount;
+        const int hx = geo.bs[0] >> 1;
+        const int xp = (int)threadIdx.x % hx, yy = ((int)threadIdx.x / hx) % geo.bs[1], zh = (int)threadIdx.x / (hx * geo.bs[1]);
+        for (int k = 0; k < ng; k++) {
+            __threadfence();
+            const int t = s_glist[k];
+            const int gx = t % nb0, gy = (t / nb0) % nb1, gz = t / (nb0 * nb1);
+            const int u0 = gx * geo.bs[0] + 2 * xp, u1 = gy * geo.bs[1] + yy;
+            if (zh < 2 && u1 < geo.Nt[1])
+                gather_cols3d_column<T, MT, 16, false, 2, true>(scratch_base, fz.g, fz.tile_items, 0, fz.ntiles, item_lo, fz.item_hi, geo,
+                                                                PeerTab{}, 0, u0, u1, zh, gz, (int)blockIdx.y);
+        }
+    }
+}
+
+// blocks no work item reaches (expect == 0) are never gathered by the fused spreader: zero them
+template <int MT>
+__global__ void __launch_bounds__(256) k_zero_empty_blocks(float2* __restrict__ g, const int* __restrict__ expect, GeomDev geo)
+{
+    const int t = blockIdx.x;
+    if (expect[t] != 0) return;
+    const int tx = t % geo.nb[0], ty = (t / geo.nb[0]) % geo.nb[1], tz = t / (geo.nb[0] * geo.nb[1]);
+    g += (size_t)blockIdx.y * geo.gsz;
+    const int n = geo.bs[0] * geo.bs[1] * geo.bs[2];
+    for (int q = threadIdx.x; q < n; q += 256) {
+        const int x = tx * geo.bs[0] + q % geo.bs[0], y = ty * geo.bs[1] + (q / geo.bs[0]) % geo.bs[1], z = tz * geo.bs[2] + q / (geo.bs[0] * geo.bs[1]);
+        if (x < geo.Nt[0] && y < geo.Nt[1] && z < geo.Nt[2]) g[((size_t)z * geo.Nt[1] + y) * geo.Nt[0] + x] = make_float2(0.f, 0.f);
     }
 }

@@ -69,7 +69,7 @@ def test_c1_full(nb, twin):
     check_pair(nb, twin, k, (256, 256), 4, T)
 
 
-@pytest.mark.parametrize("mode", [0, 7])
+@pytest.mark.parametrize("mode", [0, 7, 9])
 def test_c2_full(nb, twin, mode):
     T = np.float32
     k = O.random_nodes(2 ** 21, 3, T, seed=1)
