@@ -1,15 +1,22 @@
 # B200NFFT.jl -- Julia glue that puts libnfftb200.so behind the AbstractNFFTs plan API.
 #
-# NOTE: no `julia` binary exists in the build image or on the GPU box, so this file is syntax-reviewed only;
-# the executable twin of exactly the same calls is nfft.jl_b200/plan.py (ctypes).  Every ccall below binds an
-# entry point of include/nfftb200.h.
+# STATUS: UNTESTED.  No `julia` binary exists in the build image or on the GPU box, so this file has never been parsed
+# or run; the executable twin of exactly the same calls is nfft.jl_b200/plan.py (ctypes), which the GPU test-suite
+# drives.  Every ccall below binds an entry point of include/nfftb200.h with the argument order of that header.
 #
 # Reference interfaces mirrored (all under /root/reference):
 #   backend struct / activate! / backend()      src/NFFT.jl:40-42
 #   plan_nfft(::Backend, ::Type, k, N; kw...)   src/NFFT.jl:49-58, ext/NFFTGPUArraysExt/implementation.jl:21-30
+#   NFFTPlan fields read by tools               src/implementation.jl:16-43 (N, NOut, J, k, Ñ, dims, params, tmpVec)
+#   Base.copy                                   src/implementation.jl:45-66
 #   size_in / size_out / nodes! / mul! (x2)     AbstractNFFTs/src/interface.jl:170-211, src/implementation.jl:108-193
+#   directional plans (dims=...)                src/directional.jl:58-156, test/accuracy.jl:83-163
 #   convolve! family                            AbstractNFFTs/src/interface.jl:217-243
 #   foreign-handle finalizer precedent          Wrappers/FINUFFT.jl:52-56
+#
+# Memory safety: Julia arrays are passed to ccall as arrays (the `Ptr{T}` argument conversion roots them for the
+# duration of the call); where a raw address has to be formed first (device arrays, temporaries) the owner is kept
+# alive with GC.@preserve.
 module B200NFFT
 
 using AbstractNFFTs
@@ -26,11 +33,13 @@ struct B200Backend <: AbstractNFFTBackend end
 activate!() = AbstractNFFTs.set_active_backend!(B200NFFT)
 backend() = B200Backend()
 
+# `where` argument of the C ABI (include/nfftb200.h)
 const HOST = Cint(0)
 const DEVICE = Cint(1)
+const HOST_ASYNC = Cint(2)
 
-function check(p::Ptr{Cvoid}, st::Cint)
-    st == 0 && return
+function check(p::Ptr{Cvoid}, st::Integer)
+    st == 0 && return nothing
     msg = unsafe_string(ccall((:nfftb200_last_error, libnfftb200), Cstring, (Ptr{Cvoid},), p))
     if st == 1 || st == 2 || st == 8
         throw(ArgumentError(msg))                  # src/utils.jl:50, src/precomputation.jl:19-21, src/convolution.jl:52
@@ -41,19 +50,34 @@ function check(p::Ptr{Cvoid}, st::Cint)
     end
 end
 
-mutable struct B200NFFTPlan{T,D} <: AbstractNFFTPlan{T,D,1}
+# the subset of NFFTParams (src/implementation.jl:3-14) that tools read through `p.params`
+struct B200Params{T}
+    m::Int
+    σ::T
+    reltol::Float64
+    window::Symbol
+    LUTSize::Int64
+    precompute::PrecomputeFlags
+    blockSize::Vector{Int64}
+    blocking::Bool
+    sortNodes::Bool
+    storeDeconvolutionIdx::Bool
+end
+
+# D = number of transformed dimensions, DIM = ndims of the user's array (= D unless dims selects a subset)
+mutable struct B200NFFTPlan{T,D,DIM,AT<:AbstractArray} <: AbstractNFFTPlan{T,DIM,1}
     handle::Ptr{Cvoid}
-    N::NTuple{D,Int64}
-    NOut::NTuple{1,Int64}
+    N::NTuple{DIM,Int64}              # user-facing array size
+    NOut::Tuple                       # J in place of the first transformed dim, the others removed (src/precomputation.jl:40-50)
     J::Int64
     k::Matrix{T}
-    Ñ::NTuple{D,Int64}
+    Ñ::NTuple{D,Int64}                # oversampled grid of the transformed dims
     dims::UnitRange{Int64}
-    m::Int
-    σ::Float64
-    reltol::Float64
-    precompute::PrecomputeFlags
-    ntransforms::Int
+    params::B200Params{T}
+    ntransforms::Int                  # product of the untransformed dims (x user-requested batch)
+    device::Int
+    user_block::Union{Nothing,Vector{Int64}}
+    tmpVec::AT                        # array-type witness for NFFTTools.sdc (samplingDensity.jl:63-64); the grid itself lives in the library
 end
 
 # order of the NFFTB200_* window enum in include/nfftb200.h
@@ -62,29 +86,43 @@ const WINDOWS = (:kaiser_bessel, :gauss, :spline, :kaiser_bessel_rev, :cosh_type
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float64}) = Cint(1)
 
-function B200NFFTPlan(k::Matrix{T}, N::NTuple{D,Int}; dims::Union{Integer,UnitRange{Int64}}=1:D,
+function B200NFFTPlan(k::Matrix{T}, N::NTuple{DIM,Int}; dims::Union{Integer,UnitRange{Int64}}=1:DIM,
                       window::Symbol=:kaiser_bessel, precompute::PrecomputeFlags=POLYNOMIAL,
-                      ntransforms::Int=1, blockSize=nothing, device::Int=0,
-                      sortNodes=false, storeDeconvolutionIdx=false, blocking=true, fftflags=nothing,
-                      kwargs...) where {T<:Union{Float32,Float64},D}
-    dims == 1:D || error("GPU NFFT does not work along directions right now!")   # ext/...:35-37
-    wcode = findfirst(==(window), WINDOWS)                                        # src/windowFunctions.jl:4-19
+                      ntransforms::Int=1, blockSize=nothing, device::Int=0, arraytype::Type=Array,
+                      sortNodes=false, storeDeconvolutionIdx=true, blocking=true, fftflags=nothing,
+                      kwargs...) where {T<:Union{Float32,Float64},DIM}
+    dimsr = dims isa Integer ? (Int64(dims):Int64(dims)) : dims
+    D = length(dimsr)
+    (first(dimsr) >= 1 && last(dimsr) <= DIM) || throw(ArgumentError("dims $(dimsr) out of range for an array with $DIM dimensions"))
+    size(k, 1) == D || throw(ArgumentError("Nodes x have dimension $(size(k,1)) != $D"))   # src/precomputation.jl:19-21
+    wcode = findfirst(==(window), WINDOWS)                                                  # src/windowFunctions.jl:4-19
     wcode === nothing && error("Window $(window) not yet implemented!")
-    size(k, 1) == D || throw(ArgumentError("Nodes x have dimension $(size(k,1)) != $D"))
-    m, σ, reltol = accuracyParams(; kwargs...)                                    # AbstractNFFTs/src/misc.jl:66-81
+    m, σ, reltol = accuracyParams(; kwargs...)                                              # AbstractNFFTs/src/misc.jl:66-81
+    others = [d for d in 1:DIM if !(d in dimsr)]
+    B = ntransforms * prod(Int64[N[d] for d in others]; init=Int64(1))
+    Nt = Int64[N[d] for d in dimsr]
+    ub = blockSize === nothing ? nothing : collect(Int64, blockSize)
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    Nv = collect(Int64, N)
-    bs = blockSize === nothing ? C_NULL : pointer(collect(Int64, blockSize))
-    st = ccall((:nfftb200_plan_create, libnfftb200), Cint,
-               (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cdouble, Cint, Cint, Cint, Ptr{Int64}, Cint),
-               h, D, Nv, dtype_code(T), m, σ, wcode - 1, Int(precompute), ntransforms, bs, device)
+    st = if ub === nothing
+        ccall((:nfftb200_plan_create, libnfftb200), Cint,
+              (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cdouble, Cint, Cint, Cint, Ptr{Int64}, Cint),
+              h, D, Nt, dtype_code(T), m, σ, wcode - 1, Int(precompute), B, C_NULL, device)
+    else
+        ccall((:nfftb200_plan_create, libnfftb200), Cint,
+              (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cdouble, Cint, Cint, Cint, Ptr{Int64}, Cint),
+              h, D, Nt, dtype_code(T), m, σ, wcode - 1, Int(precompute), B, ub, device)   # `ub` is rooted by the ccall
+    end
     check(C_NULL, st)
     Ñv = zeros(Int64, D); bsv = zeros(Int64, D)
     nt = Ref{Int64}(0); lut = Ref{Int64}(0); sg = Ref{Cdouble}(0); M = Ref{Int64}(0)
     ccall((:nfftb200_get_info, libnfftb200), Cint,
           (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cdouble}, Ref{Int64}),
           h[], Ñv, bsv, nt, lut, sg, M)
-    p = B200NFFTPlan{T,D}(h[], N, (size(k, 2),), size(k, 2), k, Tuple(Ñv), 1:D, m, sg[], reltol, precompute, ntransforms)
+    J = size(k, 2)
+    params = B200Params{T}(m, T(sg[]), reltol, window, lut[], precompute, bsv, Bool(blocking), Bool(sortNodes),
+                           Bool(storeDeconvolutionIdx))
+    witness = arraytype{Complex{T},D}(undef, ntuple(_ -> 0, D))
+    p = B200NFFTPlan{T,D,DIM,typeof(witness)}(h[], N, out_size(N, dimsr, J), J, k, Tuple(Ñv), dimsr, params, B, device, ub, witness)
     finalizer(p) do q
         q.handle == C_NULL || ccall((:nfftb200_destroy, libnfftb200), Cint, (Ptr{Cvoid},), q.handle)
         q.handle = C_NULL
@@ -93,27 +131,50 @@ function B200NFFTPlan(k::Matrix{T}, N::NTuple{D,Int}; dims::Union{Integer,UnitRa
     return p
 end
 
-function AbstractNFFTs.plan_nfft(::B200Backend, ::Type{<:AbstractArray}, k::Matrix{T}, N::NTuple{D,Int}, rest...;
+# NOut of src/precomputation.jl:40-50
+function out_size(N::NTuple{DIM,Int}, dims::UnitRange{Int64}, J::Integer) where {DIM}
+    out = Int64[]
+    taken = false
+    for d in 1:DIM
+        if !(d in dims)
+            push!(out, N[d])
+        elseif !taken
+            push!(out, J); taken = true
+        end
+    end
+    return Tuple(out)
+end
+
+function AbstractNFFTs.plan_nfft(::B200Backend, arr::Type{<:AbstractArray}, k::Matrix{T}, N::NTuple{D,Int}, rest...;
                                  timing::Union{Nothing,TimingStats}=nothing, kargs...) where {T,D}
     t = @elapsed p = B200NFFTPlan(k, N, rest...; kargs...)
     timing !== nothing && (timing.pre = t)
     return p
 end
 
-AbstractNFFTs.size_in(p::B200NFFTPlan) = p.ntransforms == 1 ? p.N : (p.N..., p.ntransforms)
-AbstractNFFTs.size_out(p::B200NFFTPlan) = p.ntransforms == 1 ? p.NOut : (p.J, p.ntransforms)
+AbstractNFFTs.size_in(p::B200NFFTPlan) = p.N
+AbstractNFFTs.size_out(p::B200NFFTPlan) = p.NOut
 
 function AbstractNFFTs.nodes!(p::B200NFFTPlan{T}, k::Matrix{T}) where {T}
     st = ccall((:nfftb200_set_nodes, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{T}, Int64, Cint),
                p.handle, k, size(k, 2), HOST)
     check(p.handle, st)
-    p.k = k; p.J = size(k, 2); p.NOut = (p.J,)
+    p.k = k; p.J = size(k, 2); p.NOut = out_size(p.N, p.dims, p.J)
     return p
 end
 
-# device pointers: any array type with `pointer` living on the plan's device (CuArray) passes DEVICE
-where(::Array) = HOST
-where(::AbstractArray) = DEVICE
+# ---- where does a buffer live, and its raw address ------------------------------------------------------------
+# Any dense array type other than Array (CuArray, ...) is taken to live on the plan's device.  CUDA.jl's pointer() is
+# a CuPtr, which converts to an integer but not to Ptr{Cvoid}.
+loc(::Array) = HOST
+loc(::AbstractArray) = DEVICE
+rawptr(x::Array) = Ptr{Cvoid}(pointer(x))
+rawptr(x::AbstractArray) = Ptr{Cvoid}(UInt(pointer(x)))
+
+function same_side(a, b)
+    loc(a) == loc(b) || throw(ArgumentError("input and output must both be host arrays or both be device arrays"))
+    return loc(a)
+end
 
 function fill_timing!(p, timing::TimingStats)
     t = zeros(Cdouble, 7)
@@ -122,31 +183,79 @@ function fill_timing!(p, timing::TimingStats)
     timing.conv_adjoint, timing.fft_adjoint, timing.deconv_adjoint = t[5], t[6], t[7]
 end
 
+# ---- directional plans: bring the transformed dims to the front (batch slowest), src/directional.jl ------------
+is_plain(p::B200NFFTPlan{T,D,DIM}) where {T,D,DIM} = p.dims == 1:D      # leading dims: the library's layout already
+others(p::B200NFFTPlan{T,D,DIM}) where {T,D,DIM} = [d for d in 1:DIM if !(d in p.dims)]
+
+function to_internal_image(p::B200NFFTPlan, f)
+    is_plain(p) && return f
+    return permutedims(f, (collect(p.dims)..., others(p)...))            # (N[dims]..., N[others]...)
+end
+function from_internal_image!(f, p::B200NFFTPlan, fi)
+    is_plain(p) && return f
+    permutedims!(f, reshape(fi, (ntuple(i -> p.N[p.dims[i]], length(p.dims))..., ntuple(i -> p.N[others(p)[i]], length(others(p)))...)),
+                 invperm([collect(p.dims)..., others(p)...]))
+    return f
+end
+# user layout of fHat: the untransformed dims before dims, J, the untransformed dims after; library layout: (J, others...)
+function out_perm(p::B200NFFTPlan)
+    npre = first(p.dims) - 1
+    no = length(others(p))
+    return (collect(2:npre+1)..., 1, collect(npre+2:no+1)...)           # internal (J, o1, o2, ...) -> user order
+end
+function to_internal_out(p::B200NFFTPlan, fHat)
+    is_plain(p) && return fHat
+    return permutedims(fHat, invperm(collect(out_perm(p))))
+end
+function from_internal_out!(fHat, p::B200NFFTPlan, fi)
+    is_plain(p) && return fHat
+    o = others(p)
+    permutedims!(fHat, reshape(fi, (p.J, ntuple(i -> p.N[o[i]], length(o))...)), out_perm(p))
+    return fHat
+end
+
 function LinearAlgebra.mul!(fHat::AbstractArray{Complex{T}}, p::B200NFFTPlan{T}, f::AbstractArray{Complex{T}};
-                            verbose=false, timing::Union{Nothing,TimingStats}=nothing) where {T}
+                            verbose=false, timing::Union{Nothing,TimingStats}=nothing, async::Bool=false) where {T}
     (size_in(p) == size(f) && size_out(p) == size(fHat)) ||
         throw(DimensionMismatch("Data is not consistent with NFFTPlan"))            # src/utils.jl:98-105
+    side = same_side(f, fHat)
+    plain = is_plain(p)
+    (async && (!plain || side != HOST)) && throw(ArgumentError("async needs host arrays and a plan over the leading dims"))
+    fi = to_internal_image(p, f)
+    fo = plain ? fHat : similar(fHat, (p.J, p.ntransforms))
     ccall((:nfftb200_set_timing, libnfftb200), Cint, (Ptr{Cvoid}, Cint), p.handle, timing !== nothing)
-    st = ccall((:nfftb200_exec_forward, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
-               p.handle, pointer(f), pointer(fHat), where(fHat))
+    GC.@preserve fi fo begin
+        st = ccall((:nfftb200_exec_forward, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                   p.handle, rawptr(fi), rawptr(fo), async ? HOST_ASYNC : side)
+    end
     check(p.handle, st)
     timing !== nothing && fill_timing!(p, timing)
-    return fHat
+    return from_internal_out!(fHat, p, fo)
 end
 
 function LinearAlgebra.mul!(f::AbstractArray{Complex{T}}, pl::Adjoint{Complex{T},<:B200NFFTPlan{T}},
                             fHat::AbstractArray{Complex{T}}; verbose=false,
-                            timing::Union{Nothing,TimingStats}=nothing) where {T}
+                            timing::Union{Nothing,TimingStats}=nothing, async::Bool=false) where {T}
     p = pl.parent
     (size_in(p) == size(f) && size_out(p) == size(fHat)) ||
         throw(DimensionMismatch("Data is not consistent with NFFTPlan"))
+    side = same_side(f, fHat)
+    plain = is_plain(p)
+    (async && (!plain || side != HOST)) && throw(ArgumentError("async needs host arrays and a plan over the leading dims"))
+    hi = to_internal_out(p, fHat)
+    fo = plain ? f : similar(f, (ntuple(i -> p.N[p.dims[i]], length(p.dims))..., p.ntransforms))
     ccall((:nfftb200_set_timing, libnfftb200), Cint, (Ptr{Cvoid}, Cint), p.handle, timing !== nothing)
-    st = ccall((:nfftb200_exec_adjoint, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
-               p.handle, pointer(fHat), pointer(f), where(f))
+    GC.@preserve hi fo begin
+        st = ccall((:nfftb200_exec_adjoint, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                   p.handle, rawptr(hi), rawptr(fo), async ? HOST_ASYNC : side)
+    end
     check(p.handle, st)
     timing !== nothing && fill_timing!(p, timing)
-    return f
+    return from_internal_image!(f, p, fo)
 end
+
+"wait for every queued transform of the plan (needed after `async=true` calls before the outputs are read)"
+sync(p::B200NFFTPlan) = check(p.handle, ccall((:nfftb200_sync, libnfftb200), Cint, (Ptr{Cvoid},), p.handle))
 
 const RealOrComplex{T} = Union{T,Complex{T}}
 
@@ -158,8 +267,11 @@ function AbstractNFFTs.convolve!(p::B200NFFTPlan{T,D}, g::AbstractArray{<:RealOr
         throw(ArgumentError("Complex input g requires Complex output fHat"))        # src/convolution.jl:47-53
     cplx = eltype(fHat) <: Complex
     gg = (cplx && eltype(g) <: Real) ? Complex{T}.(g) : g
-    st = ccall((:nfftb200_convolve, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
-               p.handle, pointer(gg), pointer(fHat), cplx, where(fHat))
+    side = same_side(gg, fHat)
+    GC.@preserve gg fHat begin
+        st = ccall((:nfftb200_convolve, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
+                   p.handle, rawptr(gg), rawptr(fHat), cplx, side)
+    end
     check(p.handle, st)
     return fHat
 end
@@ -172,24 +284,33 @@ function AbstractNFFTs.convolve_transpose!(p::B200NFFTPlan{T,D}, fHat::AbstractV
         throw(ArgumentError("Complex input fHat requires Complex output g"))        # src/convolution.jl:143-149
     cplx = eltype(g) <: Complex
     ff = (cplx && eltype(fHat) <: Real) ? Complex{T}.(fHat) : fHat
-    st = ccall((:nfftb200_convolve_transpose, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
-               p.handle, pointer(ff), pointer(g), cplx, where(g))
+    side = same_side(ff, g)
+    GC.@preserve ff g begin
+        st = ccall((:nfftb200_convolve_transpose, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
+                   p.handle, rawptr(ff), rawptr(g), cplx, side)
+    end
     check(p.handle, st)
     return g
 end
 
 function AbstractNFFTs.deconvolve!(p::B200NFFTPlan{T,D}, f::AbstractArray{Complex{T},D},
                                    g::AbstractArray{Complex{T},D}) where {T,D}
-    st = ccall((:nfftb200_deconvolve, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
-               p.handle, pointer(f), pointer(g), where(g))
+    side = same_side(f, g)
+    GC.@preserve f g begin
+        st = ccall((:nfftb200_deconvolve, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                   p.handle, rawptr(f), rawptr(g), side)
+    end
     check(p.handle, st)
     return
 end
 
 function AbstractNFFTs.deconvolve_transpose!(p::B200NFFTPlan{T,D}, g::AbstractArray{Complex{T},D},
                                              f::AbstractArray{Complex{T},D}) where {T,D}
-    st = ccall((:nfftb200_deconvolve_transpose, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
-               p.handle, pointer(g), pointer(f), where(f))
+    side = same_side(g, f)
+    GC.@preserve f g begin
+        st = ccall((:nfftb200_deconvolve_transpose, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                   p.handle, rawptr(g), rawptr(f), side)
+    end
     check(p.handle, st)
     return
 end
@@ -206,20 +327,54 @@ function permutation(p::B200NFFTPlan)
     return perm, ts
 end
 
-function Base.show(io::IO, p::B200NFFTPlan{T,D}) where {T,D}
+"device address of the oversampled grid (the reference's p.tmpVec), e.g. for unsafe_wrap(CuArray, CuPtr{Complex{T}}(UInt(ptr)), p.Ñ)"
+function grid_pointer(p::B200NFFTPlan)
+    ptr = Ref{Ptr{Cvoid}}(C_NULL)
+    check(p.handle, ccall((:nfftb200_get_grid, libnfftb200), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), p.handle, ptr))
+    return ptr[]
+end
+
+function Base.show(io::IO, p::B200NFFTPlan)
     print(io, "B200NFFTPlan with ", p.J, " sampling points for an input array of size", p.N,
           " and an output array of size", p.NOut, " with dims ", p.dims)
 end
 
-# a plan is single-stream state (src/implementation.jl:26,36); copy re-plans like Base.copy(::NFFTPlan) (:45-66)
-Base.copy(p::B200NFFTPlan{T,D}) where {T,D} =
-    B200NFFTPlan(p.k, p.N; m=p.m, σ=p.σ, precompute=p.precompute, ntransforms=p.ntransforms)
+# a plan is single-stream state (src/implementation.jl:26,36); copy re-plans with every parameter of the original, like
+# Base.copy(::NFFTPlan) (:45-66): window, precompute flag, blockSize, dims, device and array type are all carried over
+function Base.copy(p::B200NFFTPlan{T,D,DIM,AT}) where {T,D,DIM,AT}
+    batch = p.ntransforms ÷ prod(Int64[p.N[d] for d in others(p)]; init=Int64(1))
+    return B200NFFTPlan(p.k, p.N; dims=p.dims, m=p.params.m, σ=Float64(p.params.σ), window=p.params.window,
+                        precompute=p.params.precompute, ntransforms=batch, blockSize=p.user_block, device=p.device,
+                        arraytype=Base.typename(AT).wrapper, sortNodes=p.params.sortNodes, blocking=p.params.blocking)
+end
+
+# ---- multi-GPU: one process per GPU, the communicator is bootstrapped from a 128-byte id (include/nfftb200.h) ----
+const SHARD_BATCH = Cint(1)
+const SHARD_NODES = Cint(2)
+
+"128-byte NCCL unique id; create it on rank 0 and broadcast it with the host's own transport (MPI.jl, Distributed, ...)"
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(C_NULL, ccall((:nfftb200_comm_unique_id, libnfftb200), Cint, (Ptr{UInt8},), id))
+    return id
+end
+
+"collective: attach the plan to a communicator of `nranks` processes; mode = SHARD_BATCH or SHARD_NODES.  Call nodes! afterwards."
+function comm_init!(p::B200NFFTPlan, id::Vector{UInt8}, rank::Integer, nranks::Integer, mode::Integer)
+    length(id) == 128 || throw(ArgumentError("the communicator id has 128 bytes"))
+    check(p.handle, ccall((:nfftb200_comm_init, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint, Cint),
+                          p.handle, id, rank, nranks, mode))
+    return p
+end
+
+"true if the node-sharded plan exchanges grid data over CUDA-IPC peer memory inside the kernels (no NCCL collective on the path)"
+comm_is_fused(p::B200NFFTPlan) = ccall((:nfftb200_comm_is_fused, libnfftb200), Cint, (Ptr{Cvoid},), p.handle) != 0
 
 # ---- sampling density compensation, NFFTTools/src/samplingDensity.jl:59-155 ---------------------------------
 "sdc(p; iters=20): Pipe-Menon weights, all iterations on the device (NFFTTools.sdc works too, through convolve!)"
-function sdc(p::B200NFFTPlan{T,D}; iters::Int=20) where {T,D}
+function sdc(p::B200NFFTPlan{T}; iters::Int=20) where {T}
     w = Vector{T}(undef, p.J)
-    check(p.handle, ccall((:nfftb200_sdc, libnfftb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint),
+    check(p.handle, ccall((:nfftb200_sdc, libnfftb200), Cint, (Ptr{Cvoid}, Cint, Ptr{T}, Cint),
                           p.handle, iters, w, HOST))
     return w
 end
@@ -229,8 +384,10 @@ end
 function calculateToeplitzKernel!(f::AbstractArray{Complex{T},D}, p::B200NFFTPlan{T,D}, tr::Matrix{T}, fftplan=nothing) where {T,D}
     AbstractNFFTs.nodes!(p, tr)
     size(f) == p.N || throw(DimensionMismatch("Toeplitz kernel has size $(size(f)) != $(p.N)"))
-    check(p.handle, ccall((:nfftb200_toeplitz_kernel, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint),
-                          p.handle, pointer(f), where(f)))
+    GC.@preserve f begin
+        st = ccall((:nfftb200_toeplitz_kernel, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), p.handle, rawptr(f), loc(f))
+    end
+    check(p.handle, st)
     return f
 end
 
@@ -249,23 +406,28 @@ end
 function ToeplitzOperator(λ::AbstractArray{Complex{T},D}; ntransforms::Int=1, device::Int=0) where {T,D}
     shape = size(λ) .÷ 2
     h = Ref{Ptr{Cvoid}}(C_NULL)
+    shp = collect(Int64, shape)
     check(C_NULL, ccall((:nfftb200_toeplitz_create, libnfftb200), Cint,
                         (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cint),
-                        h, D, collect(Int64, shape), dtype_code(T), ntransforms, device))
+                        h, D, shp, dtype_code(T), ntransforms, device))
     op = ToeplitzOperator{T,D}(h[], shape)
     finalizer(op) do q
         q.handle == C_NULL || ccall((:nfftb200_toeplitz_destroy, libnfftb200), Cint, (Ptr{Cvoid},), q.handle)
         q.handle = C_NULL
     end
-    check(C_NULL, ccall((:nfftb200_toeplitz_set_kernel, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint),
-                        op.handle, pointer(λ), where(λ)))
+    GC.@preserve λ begin
+        st = ccall((:nfftb200_toeplitz_set_kernel, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), op.handle, rawptr(λ), loc(λ))
+    end
+    check(C_NULL, st)
     return op
 end
 
 "convolveToeplitzKernel!(y, λ) with the plans and work arrays held by `op`"
 function convolveToeplitzKernel!(y::AbstractArray{Complex{T}}, op::ToeplitzOperator{T}) where {T}
-    check(C_NULL, ccall((:nfftb200_toeplitz_apply, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint),
-                        op.handle, pointer(y), where(y)))
+    GC.@preserve y begin
+        st = ccall((:nfftb200_toeplitz_apply, libnfftb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), op.handle, rawptr(y), loc(y))
+    end
+    check(C_NULL, st)
     return y
 end
 convolveToeplitzKernel!(y::AbstractArray{Complex{T},D}, λ::AbstractArray{Complex{T},D}) where {T,D} =
