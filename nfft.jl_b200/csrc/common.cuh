@@ -241,6 +241,13 @@ inline bool nfftb_tiled_ok(const nfftb200_plan* p)
     return p->kernel_mode != 1 && !(p->precompute == NFFTB200_FULL && p->window != NFFTB200_KAISER_BESSEL);
 }
 
+// kernel modes that run the (tile, bin)-ordered register-window kernels of lean.cu where they apply: 0 = auto, 3 = auto
+// without the TMA tensor-map load, 8 = explicit, 11 = fused spread + gather experiment, 12 = compact tile layout
+inline bool nfftb_lean_mode(const nfftb200_plan* p)
+{
+    return p->kernel_mode == 0 || p->kernel_mode == 3 || p->kernel_mode == 8 || p->kernel_mode == 11 || p->kernel_mode == 12;
+}
+
 template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
 {
     WinDev<T> w;

@@ -364,7 +364,7 @@ int peer_interp(nfftb200_plan* p, const SlabTab& st, void* fhat, int t_lo, int t
     if (smem > 227 * 1024 || geo.bs[0] + 2 * MT > 64 || geo.bs[1] + 2 * MT > 32) return -1;
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
-    if (sizeof(T) == 4 && (p->kernel_mode == 0 || p->kernel_mode == 8 || p->kernel_mode == 11)) {   // (tile, bin)-ordered register windows, slab-direct form
+    if (sizeof(T) == 4 && nfftb_lean_mode(p)) {   // (tile, bin)-ordered register windows, slab-direct form
         if (p->timing) cudaEventRecord(p->evk[3], p->stream);
         const int r = nfftb_interp_lean(p, nullptr, fhat, 1, t_lo, t_hi, &st);
         if (r >= 0) {
@@ -471,7 +471,7 @@ int interp_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int is_compl
         const int r = nfftb_interp_2d(p, g, fhat, B, t_lo, t_hi);
         if (r >= 0) return r;
     }
-    if (sizeof(T) == 4 && nfftb_tiled_ok(p) && is_complex && p->D == 3 && (p->kernel_mode == 0 || p->kernel_mode == 8 || p->kernel_mode == 11)) {
+    if (sizeof(T) == 4 && nfftb_tiled_ok(p) && is_complex && p->D == 3 && nfftb_lean_mode(p)) {
         const int r = nfftb_interp_lean(p, g, fhat, B, t_lo, t_hi, nullptr);      // lean.cu: (tile, bin)-ordered register windows
         if (r >= 0) return r;
     }

@@ -11,6 +11,8 @@
 //   * window origins are clamped into the padded tile, so no load is bounds-checked.
 // Float32 only (packed FFMA2 arithmetic); other types keep the default kernels.
 #pragma once
+#include <cuda.h>
+
 #include "bin_common.cuh"
 #include "interp_bin.cuh"
 
@@ -23,22 +25,63 @@ template <int MT, int W> struct LeanGeom {
     static_assert(W == 8, "lane = (y, z) row mapping below assumes W = 8 (two passes of 32 rows)");
 };
 
+// Two shared-memory layouts of the padded tile:
+//   compact: row / plane pitches searched for conflict-free 8-byte window loads (bin_make_geom), cp.async staging;
+//   WIDE   : rows of LEAN_WIDE_PITCH = 26 cells starting at the even cell x0 - (x0 & 1), planes of 26 * PY cells -- the
+//            dense image of ONE TMA tensor-map box (cp.async.bulk.tensor, SASS UTMALDG), which is how interior tiles
+//            are staged (the box start must be 16-byte aligned, hence the even start; tiles that wrap periodically are
+//            staged row by row with cp.async into the same layout).  A pitch of 26 cells = 13 sixteen-byte granules keeps
+//            the 8 lanes of a quarter-warp (8 consecutive y rows) on 8 distinct granules, so the window is loaded with
+//            conflict-free LDS.128: 4 per row when the window starts on an even cell, 5 otherwise.
+constexpr int LEAN_WIDE_PITCH = 26;
+
 template <int MT, int W> struct LeanInterpLayout {
     static constexpr int RW = 4 * W;                         // record: wx[W] | wy[W] | wz[W] | window origin (3 ints), pad
-    static bool make(const int* bs, BinGeom& bg) { return bin_make_geom<float, MT, W>(bs, bg); }
-    static size_t bytes(const BinGeom& bg)
+    static bool make(const int* bs, BinGeom& bg, bool wide)
+    {
+        if (!bin_make_geom<float, MT, W>(bs, bg)) return false;
+        if (wide) {
+            if (bs[0] + 2 * MT + 1 > LEAN_WIDE_PITCH) return false;
+            bg.PXp = LEAN_WIDE_PITCH;
+            bg.PL = LEAN_WIDE_PITCH * (bs[1] + 2 * MT);
+            bg.PNs = bg.PL * (bs[2] + 2 * MT);
+        }
+        return true;
+    }
+    // lut_floats: entries of the LINEAR window table staged in shared memory (0: none)
+    static size_t bytes(const BinGeom& bg, int lut_floats)
     {
         return sizeof(float2) * (size_t)bg.PNs + sizeof(float) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW +
-               sizeof(float) * NFFTB_BIN_WARPS * 2 * NFFTB_BIN_ROUND + 16;
+               sizeof(float) * NFFTB_BIN_WARPS * 2 * NFFTB_BIN_ROUND + sizeof(float) * (size_t)((lut_floats + 3) & ~3) + 16 + 16;
     }
 };
 
-template <int MT, int W, bool PEER>
+// mbarrier wait with a label that stays unique when the function is inlined several times
+__device__ __forceinline__ void lean_mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done = 0;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS UBLKCP), completion on an mbarrier; 16-byte granular
+__device__ __forceinline__ void lean_bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// lut_floats > 0 (LINEAR windows): the interpolation table is staged in shared memory by one bulk copy and eval_taps
+// reads it there instead of issuing two global loads per tap.
+template <int MT, int W, bool PEER, bool WIDE>
 __global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, 2)
 k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const float* __restrict__ xs2,
               const int32_t* __restrict__ perm2, const int32_t* __restrict__ bin_start, const int32_t* __restrict__ items,
               int item_lo, long long M, GeomDev geo, WinDev<float> win, const __grid_constant__ PolyParam<float, MT> pp,
-              BinGeom bg, const __grid_constant__ SlabTab slabs)
+              BinGeom bg, const __grid_constant__ SlabTab slabs, const __grid_constant__ CUtensorMap tmap, int use_tma,
+              int lut_floats)
 {
     using T = float;
     using C = float2;
@@ -47,10 +90,12 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
     constexpr int NWARP = NFFTB_BIN_WARPS, RND = NFFTB_BIN_ROUND, NP = 2;
     static_assert(RND == 8, "rounds of 8 nodes");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     C* P = reinterpret_cast<C*>(smem_raw);                                          // [PZ][PL] padded tile
     T* rec = reinterpret_cast<T*>(P + bg.PNs);                                      // [NWARP][RND][RW]
     T* res = rec + NWARP * RND * RW;                                                // [NWARP][2 * RND]
+    T* lut = res + NWARP * 2 * RND;                                                 // [lut_floats, rounded up to 4]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(lut + ((lut_floats + 3) & ~3));
 
     const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
     const int tile_id = item[0];
@@ -68,8 +113,24 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
     T* myrec = rec + warp * RND * RW;
     T* myres = res + warp * 2 * RND;
 
-    // ---- toBlock!: the padded tile (periodic wrap per row), asynchronously
-    {
+    // ---- toBlock!: the padded tile.  WIDE: interior tiles by one TMA box load, the others (periodic wrap) row by row.
+    const int xs_ = WIDE ? ((cx0 - MT) & 1) : 0;                              // tile cell X sits at row offset X + xs_
+    bool tma_tile = false;
+    if (WIDE && !PEER) {
+        const int x0 = cx0 - MT, y0 = cy0 - MT, z0 = cz0 - MT;
+        tma_tile = use_tma && x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + PX <= geo.Nt[0] && y0 + PY <= geo.Nt[1] && z0 + PZ <= geo.Nt[2];
+    }
+    const bool use_bar = tma_tile || lut_floats > 0;
+    if (use_bar && threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        unsigned bytes = 0;
+        if (tma_tile) bytes += (unsigned)(sizeof(C) * LEAN_WIDE_PITCH * PY * PZ);
+        if (lut_floats > 0) bytes += (unsigned)(sizeof(T) * ((lut_floats + 3) & ~3));
+        mbar_expect_tx(mbar, bytes);
+        if (tma_tile) tma_load_4d(P, &tmap, mbar, 2 * (cx0 - MT - xs_), cy0 - MT, cz0 - MT, (int)blockIdx.y);
+        if (lut_floats > 0) lean_bulk_g2s(lut, win.lin, (unsigned)(sizeof(T) * ((lut_floats + 3) & ~3)), mbar);
+    }
+    if (!tma_tile) {
         const int x0 = cx0 - MT, y0 = cy0 - MT, z0 = cz0 - MT;
         const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
         const int xg0 = wrapc(x0 + lane, geo.Nt[0], fw), xg1 = wrapc(x0 + lane + 32, geo.Nt[0], fw);
@@ -85,7 +146,7 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
             gz *= geo.Nt[1];
             for (int y = warp; y < PY; y += NWARP) {
                 const C* src = gb + (size_t)(gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
-                C* dst = P + (z * PL + y * PXp + lane);
+                C* dst = P + (z * PL + y * PXp + lane + xs_);
                 if (on0) cp_async_cell(dst, src + xg0);
                 if (on1) cp_async_cell(dst + 32, src + xg1);
             }
@@ -105,7 +166,10 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
     int jnext = (nl0 + lane < nl1 && lane < RND) ? perm2[nl0 + lane] : 0;
 
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();                                                         // tile resident
+    __syncthreads();                                                         // tile resident (cp.async part), mbarrier initialised
+    if (use_bar) lean_mbar_wait(mbar, 0);                                    // TMA box and / or the window table have landed
+    WinDev<T> winl = win;
+    if (lut_floats > 0) winl.lin = lut;
 
     BinRow<T, W> win_row[NP];
     int c0 = -1, c1 = -1, c2 = -1;                                           // origin of the resident window
@@ -122,7 +186,7 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
             T ks;
             const int c = node_cell<T>(x, wNt, ks);
             T w[L];
-            eval_taps<T, MT>(win, pp, ks, c, w);
+            eval_taps<T, MT>(winl, pp, ks, c, w);
             const int lc = c - wc0;                                          // first tap at padded coordinate lc + 1
             const int wo = min(1 + bin_first<W, G>(bin_of<W, G>(lc)), wmax);
             const int dl = lc + 1 - wo;                                      // first tap inside the window
@@ -143,11 +207,35 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
                 const int4 org = *reinterpret_cast<const int4*>(rn + 3 * W);
                 if (org.x != c0 || org.y != c1 || org.z != c2) {             // warp-uniform: first node of a bin
                     c0 = org.x; c1 = org.y; c2 = org.z;
-                    const C* row = P + ((c2 + rowz) * PL + (c1 + rowy) * PXp + c0);
+                    const C* row = P + ((c2 + rowz) * PL + (c1 + rowy) * PXp + c0 + xs_);
+                    if (WIDE) {
+                        if (((c0 + xs_) & 1) == 0) {                         // warp-uniform: window starts on a 16-byte boundary
 #pragma unroll
-                    for (int p = 0; p < NP; p++) {
+                            for (int p = 0; p < NP; p++) {
 #pragma unroll
-                        for (int k = 0; k < W; k++) win_row[p].set(k, row[p * 4 * PL + k]);
+                                for (int k = 0; k < W / 2; k++) {
+                                    const float4 u = *reinterpret_cast<const float4*>(row + p * 4 * PL + 2 * k);
+                                    win_row[p].set(2 * k, make_float2(u.x, u.y)); win_row[p].set(2 * k + 1, make_float2(u.z, u.w));
+                                }
+                            }
+                        } else {                                             // one cell earlier: 5 aligned loads, the ends discarded
+#pragma unroll
+                            for (int p = 0; p < NP; p++) {
+                                float4 u[W / 2 + 1];
+#pragma unroll
+                                for (int k = 0; k < W / 2 + 1; k++) u[k] = *reinterpret_cast<const float4*>(row + p * 4 * PL - 1 + 2 * k);
+#pragma unroll
+                                for (int k = 0; k < W / 2; k++) {
+                                    win_row[p].set(2 * k, make_float2(u[k].z, u[k].w)); win_row[p].set(2 * k + 1, make_float2(u[k + 1].x, u[k + 1].y));
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < NP; p++) {
+#pragma unroll
+                            for (int k = 0; k < W; k++) win_row[p].set(k, row[p * 4 * PL + k]);
+                        }
                     }
                 }
                 T wx[W];

@@ -46,7 +46,8 @@ int upload_table(nfftb200_plan* p, const std::vector<double>& h, void** d)
 {
     if (*d) { cudaFree(*d); *d = nullptr; }
     if (h.empty()) return NFFTB200_OK;
-    CUDA_TRY(p, cudaMalloc(d, h.size() * p->esz()));
+    CUDA_TRY(p, cudaMalloc(d, h.size() * p->esz() + 16));          // slack: bulk (TMA) copies of a table are 16-byte granular
+    CUDA_TRY(p, cudaMemset(*d, 0, h.size() * p->esz() + 16));
     if (p->dtype == NFFTB200_F32) {
         std::vector<float> t(h.size());
         for (size_t i = 0; i < h.size(); i++) t[i] = (float)h[i];

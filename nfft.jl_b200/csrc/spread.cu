@@ -673,7 +673,7 @@ int peer_spread(nfftb200_plan* p, const void* fhat, void* scratch, int t_lo, int
     const size_t smem = lay.bytes();
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
-    if (sizeof(T) == 4 && (p->kernel_mode == 0 || p->kernel_mode == 8 || p->kernel_mode == 11)) {   // (tile, bin)-ordered register windows, same scratch layout
+    if (sizeof(T) == 4 && nfftb_lean_mode(p)) {   // (tile, bin)-ordered register windows, same scratch layout
         const int r = nfftb_spread_lean(p, fhat, nullptr, scratch, 1, t_lo, t_hi);
         if (r >= 0) return r;
     }
@@ -751,7 +751,7 @@ int spread_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int is_compl
             return r;
         }
     }
-    if (sizeof(T) == 4 && i_hi > i_lo && nfftb_tiled_ok(p) && is_complex && p->D == 3 && (p->kernel_mode == 0 || p->kernel_mode == 8 || p->kernel_mode == 11)) {
+    if (sizeof(T) == 4 && i_hi > i_lo && nfftb_tiled_ok(p) && is_complex && p->D == 3 && nfftb_lean_mode(p)) {
         const int r = nfftb_spread_lean(p, fhat, g, nullptr, B, t_lo, t_hi);    // lean.cu: (tile, bin)-ordered register windows
         if (r >= 0) return r;
     }

@@ -25,9 +25,10 @@
 template <int MT, int W> struct LeanSpreadLayout {
     static constexpr int RW = 4 * W + 4;                     // record: wx[W] | wy[W] | (wz * v)[W] re, im | window origin (3 ints)
     static bool make(const int* bs, BinGeom& bg) { return bin_make_geom<float, MT, W>(bs, bg); }
-    static size_t bytes(const BinGeom& bg)
+    static size_t bytes(const BinGeom& bg, int lut_floats)
     {
-        return sizeof(float2) * (size_t)bg.PNs + sizeof(float) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW + 64 + 16;
+        return sizeof(float2) * (size_t)bg.PNs + sizeof(float) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW + 64 +
+               sizeof(float) * (size_t)((lut_floats + 3) & ~3) + 16 + 16;
     }
 };
 
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(NFFTB_BIN_WARPS * 32, 2)
 k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, const float* __restrict__ xs2,
               const int32_t* __restrict__ perm2, const int32_t* __restrict__ bin_start, const int32_t* __restrict__ items,
               int item_lo, long long M, GeomDev geo, WinDev<float> win, const __grid_constant__ PolyParam<float, MT> pp,
-              BinGeom bg, const __grid_constant__ LeanFuse fz)
+              BinGeom bg, const __grid_constant__ LeanFuse fz, int lut_floats)
 {
     using T = float;
     using C = float2;
@@ -73,7 +74,9 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* P = reinterpret_cast<C*>(smem_raw);                                          // [PZ][PL] padded tile
     T* rec = reinterpret_cast<T*>(P + bg.PNs);                                      // [NWARP][RND][RW]
-    int* done = reinterpret_cast<int*>(rec + NWARP * RND * RW);                     // [NWARP] colours finished per warp
+    int* done = reinterpret_cast<int*>(rec + NWARP * RND * RW);                     // [NWARP] colours finished per warp (64 bytes)
+    T* lut = reinterpret_cast<T*>(done + 16);                                       // [lut_floats, rounded up to 4]: LINEAR window table
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(lut + ((lut_floats + 3) & ~3));
 
     const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
     const int tile_id = item[0];
@@ -100,6 +103,12 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
     const int wNt = wd == 0 ? geo.Nt[0] : (wd == 1 ? geo.Nt[1] : geo.Nt[2]);
     const int wc0 = wd == 0 ? cx0 : (wd == 1 ? cy0 : cz0);
 
+    if (lut_floats > 0 && threadIdx.x == 0) {                                // stage the window table: one bulk (TMA) copy
+        const unsigned bytes = (unsigned)(sizeof(T) * ((lut_floats + 3) & ~3));
+        mbar_init(mbar, 1);
+        mbar_expect_tx(mbar, bytes);
+        lean_bulk_g2s(lut, win.lin, bytes, mbar);
+    }
     // first round's inputs in flight while the tile is zeroed
     T xnext = (T)0;
     C vnext = make_float2(0.f, 0.f);
@@ -114,6 +123,8 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
         if (threadIdx.x < NWARP) done[threadIdx.x] = 0;
     }
     __syncthreads();
+    WinDev<T> winl = win;
+    if (lut_floats > 0) { lean_mbar_wait(mbar, 0); winl.lin = lut; }
 
     int rbase = nl0 - RND;                                                   // list index of the resident round
     int pos = nl0;                                                           // next node of this warp's list
@@ -142,7 +153,7 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
                         T ks;
                         const int cc = node_cell<T>(x, wNt, ks);
                         T w[L];
-                        eval_taps<T, MT>(win, pp, ks, cc, w);
+                        eval_taps<T, MT>(winl, pp, ks, cc, w);
                         const int lc = cc - wc0;                             // first tap at padded coordinate lc + 1
                         const int wo = 1 + bin_first<W, G>(bin_of<W, G>(lc));
                         const int dl = lc + 1 - wo;                          // first tap inside the window, in [0, G)

@@ -32,3 +32,33 @@ def test_bin_kernels_parity(case):
     import try_bin_kernels as tb
     name, N, M, T, m, kw = case
     assert tb.parity_case(name, N, M, T, m, **kw), tb.out_lines[-1]
+
+
+@pytest.mark.parametrize("m", [2, 3])
+@pytest.mark.parametrize("pre", ["POLYNOMIAL", "LINEAR", "FULL", "TENSOR"])
+@pytest.mark.parametrize("mode", [0, 3, 12, 11])
+def test_lean_kernels_window_modes_and_layouts(m, pre, mode):
+    """the default (tile, bin)-ordered register-window kernels (kernel_mode 0 for Float32 3-D m <= 3) against the oracle
+    for every window evaluation mode -- LINEAR stages its table in shared memory with a bulk (TMA) copy -- and for the
+    three tile layouts of the interpolator: 0 = wide layout, interior tiles by one TMA box load; 3 = wide layout,
+    cp.async only; 12 = compact layout; 11 = the fused spread + gather experiment.  48^3 has interior and wrapping tiles."""
+    import torch
+    import nfft_jl_b200 as nb
+    from oracle import nfft_oracle as O
+    T, N, M = np.float32, (48, 40, 56), 60000
+    k = O.random_nodes(M, 3, T, seed=17)
+    k[:4000] = (k[:4000] * T(0.05)).astype(T)                   # a crowded tile: several rounds per bin
+    flag = getattr(nb.PrecomputeFlags, pre)
+    p = nb.plan_nfft(torch.from_numpy(np.ascontiguousarray(k.T)).cuda(), N, m=m, σ=2.0, precompute=flag)
+    p.set_kernel_mode(mode)
+    po = O.OraclePlan(k, N, m=m, sigma=2.0, precompute=int(flag), blockSize=p.params.blockSize)
+    f = O.random_complex(N, T, 2)
+    fh = O.random_complex(M, T, 3)
+
+    def rel(a, b):
+        a = np.asarray(a).ravel().astype(np.complex128); b = np.asarray(b).ravel().astype(np.complex128)
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    fwd = np.array(p * f)
+    adj = np.array(p.adjoint() * fh)
+    assert rel(fwd, po.forward(f)) <= 1e-5 and rel(adj, po.adjoint(fh)) <= 1e-5
+    assert np.array_equal(fwd, np.array(p * f)) and np.array_equal(adj, np.array(p.adjoint() * fh))   # bit-reproducible
