@@ -157,6 +157,8 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
  *   8 = force the (tile, bin)-ordered register-window kernels (csrc/spread_lean.cuh, csrc/interp_lean.cuh): Float32,
  *       3-D, m = 2 or 3, tiles of at most 16 cells.  Mode 0 already selects them where they apply.
  *   9 = the round-1 default: warp-private sub-tile spreader / row-per-lane interpolator for every 3-D plan.
+ *  13 = mode 8 with thread-block clusters of two x-adjacent tiles that merge their shared halo through distributed
+ *       shared memory and write one 38-column block to the scratch (experiment).
  *  12 = mode 8 with the compact tile layout in the interpolator (no TMA box load, 8-byte window loads).
  *  11 = mode 8 with the gather pass fused into the spreader ("last arriver gathers", csrc/spread_lean.cuh); measured
  *       slower than spread + separate gather on B200, kept as an experiment. */

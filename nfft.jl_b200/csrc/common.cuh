@@ -142,6 +142,8 @@ struct nfftb200_plan {
     int32_t* d_ready = nullptr;      // B * ntiles, zeroed before every fused spread
     std::vector<int32_t> h_expect;
     int64_t cap_ready = 0;
+    int32_t* d_pair_items = nullptr; // cluster-pair experiment (kernel_mode 13): identity item table of the x-pairs of tiles
+    int64_t cap_pair_items = 0;
 
     // sort scratch
     uint32_t* d_keys[2] = {nullptr, nullptr};
@@ -242,10 +244,10 @@ inline bool nfftb_tiled_ok(const nfftb200_plan* p)
 }
 
 // kernel modes that run the (tile, bin)-ordered register-window kernels of lean.cu where they apply: 0 = auto, 3 = auto
-// without the TMA tensor-map load, 8 = explicit, 11 = fused spread + gather experiment, 12 = compact tile layout
+// without the TMA tensor-map load, 8 = explicit, 11 = fused spread + gather experiment, 12 = compact tile layout, 13 = cluster-pair DSMEM halo experiment
 inline bool nfftb_lean_mode(const nfftb200_plan* p)
 {
-    return p->kernel_mode == 0 || p->kernel_mode == 3 || p->kernel_mode == 8 || p->kernel_mode == 11 || p->kernel_mode == 12;
+    return p->kernel_mode == 0 || p->kernel_mode == 3 || p->kernel_mode == 8 || (p->kernel_mode >= 11 && p->kernel_mode <= 13);
 }
 
 template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
@@ -270,7 +272,8 @@ int nfftb_ensure_bins(nfftb200_plan* p, int W, int G);
 // lean.cu (kernel_mode 8, Float32 3-D): -1 when the kernels do not apply; scratch_override / slabs select the node-sharded forms
 int nfftb_spread_lean(nfftb200_plan* p, const void* fhat, void* g, void* scratch_override, int B, int t_lo, int t_hi);
 int nfftb_interp_lean(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo, int t_hi, const SlabTab* slabs);
-int nfftb_gather_scratch(nfftb200_plan* p, const void* scratch, void* g, int B, int t_lo, int t_hi, int item_lo, int item_hi);   // spread.cu                          // sort.cu: (tile, bin) order for kernel_mode 8
+int nfftb_gather_scratch(nfftb200_plan* p, const void* scratch, void* g, int B, int t_lo, int t_hi, int item_lo, int item_hi,
+                         const GeomDev* geo_override = nullptr, const int32_t* items_override = nullptr);                          // spread.cu                          // sort.cu: (tile, bin) order for kernel_mode 8
 int nfftb_deconvolve(nfftb200_plan* p, const void* d_f, void* d_g, int B);      // deconv.cu
 int nfftb_deconvolve_transpose(nfftb200_plan* p, const void* d_g, void* d_f, int B);
 // t_lo/t_hi: half-open range of reference tiles ("blocks") whose nodes are processed

@@ -3,6 +3,7 @@
 #include <cuda.h>
 
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "window.cuh"
@@ -80,6 +81,46 @@ int spread_lean(nfftb200_plan* p, const void* fhat, void* g, void* scratch_overr
         p->launches += 3;
         if (p->timing) { cudaEventRecord(p->evk[2], st); p->pending_k |= 1; }
         CUDA_TRY(p, cudaGetLastError());
+        return NFFTB200_OK;
+    }
+    // cluster-pair experiment (kernel_mode 13): needs one work item per tile, every tile non-empty, whole tiles, an even
+    // number of tiles along x, the whole grid in one launch
+    bool pair = !scratch_override && p->kernel_mode == 13 && t_lo == 0 && t_hi == p->ntiles && (geo.nb[0] % 2 == 0) &&
+                geo.Nt[0] % (2 * geo.bs[0]) == 0 && p->nitems == p->ntiles && geo.bs[2] == 16 && geo.Nt[2] % 16 == 0;
+    if (pair) {
+        const int npairs = (int)(p->ntiles / 2);
+        if (npairs + 1 > p->cap_pair_items) {
+            if (p->d_pair_items) cudaFree(p->d_pair_items);
+            p->d_pair_items = nullptr; p->cap_pair_items = 0;
+            CUDA_TRY(p, cudaMalloc((void**)&p->d_pair_items, sizeof(int32_t) * (size_t)(npairs + 1)));
+            std::vector<int32_t> iota((size_t)npairs + 1);
+            for (int i = 0; i <= npairs; i++) iota[(size_t)i] = i;
+            CUDA_TRY(p, cudaMemcpy(p->d_pair_items, iota.data(), sizeof(int32_t) * iota.size(), cudaMemcpyHostToDevice));
+            p->cap_pair_items = npairs + 1;
+        }
+        if (p->timing) { cudaEventRecord(p->evk[0], st); cudaEventRecord(p->evk[1], st); }
+        auto kp = k_spread_lean<MT, W, false, true>;
+        CUDA_TRY(p, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(item_hi - item_lo, B);
+        cfg.blockDim = dim3(NFFTB_BIN_WARPS * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(p, cudaLaunchKernelEx(&cfg, kp, (const C*)fhat, (C*)scratch, (const T*)p->d_xs2, (const int32_t*)p->d_perm2,
+                                       (const int32_t*)p->d_bin_start, (const int32_t*)p->d_items, item_lo, (long long)p->M, geo, make_win<T>(p),
+                                       make_poly_param<T, MT>(p), bg, LeanFuse{}, lut_floats));
+        p->launches++;
+        if (p->timing) { cudaEventRecord(p->evk[5], st); p->have_gather_ev = true; }
+        GeomDev gp = geo;
+        gp.bs[0] = 2 * geo.bs[0]; gp.nb[0] = geo.nb[0] / 2;
+        gp.inv_bs[0] = (unsigned)((0x100000000ull + (unsigned long long)gp.bs[0] - 1) / (unsigned long long)gp.bs[0]);
+        ST_TRY(nfftb_gather_scratch(p, scratch, g, B, 0, npairs, 0, npairs, &gp, p->d_pair_items));
+        if (p->timing) { cudaEventRecord(p->evk[2], st); p->pending_k |= 1; }
         return NFFTB200_OK;
     }
     if (p->timing) { cudaEventRecord(p->evk[0], st); cudaEventRecord(p->evk[1], st); }

@@ -413,7 +413,7 @@ int nfftb200_destroy(nfftb200_plan* p)
     void* bufs[] = {p->d_hat_inv, p->d_poly, p->d_lin, p->d_grid, p->d_xs, p->d_tile_start, p->d_keys[0],
                     p->d_keys[1], p->d_vals[0], p->d_vals[1], p->d_hist, p->d_flag, p->d_stage_f,
                     p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab, p->d_tilebuf, p->d_items, p->d_tile_items,
-                    p->d_xs2, p->d_perm2, p->d_bin_start, p->d_expect, p->d_ready};
+                    p->d_xs2, p->d_perm2, p->d_bin_start, p->d_expect, p->d_ready, p->d_pair_items};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 4; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     for (int i = 0; i < 6; i++) if (p->evk[i]) cudaEventDestroy(p->evk[i]);

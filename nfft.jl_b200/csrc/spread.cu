@@ -848,12 +848,14 @@ int nfftb_peer_gather(nfftb200_plan* p, void* d_slab, int layer_lo, int nlayers,
 }
 
 // gather pass over a scratch of padded tiles written by any of the 3-D spreaders (used by lean.cu)
-int nfftb_gather_scratch(nfftb200_plan* p, const void* scratch, void* g, int B, int t_lo, int t_hi, int item_lo, int item_hi)
+int nfftb_gather_scratch(nfftb200_plan* p, const void* scratch, void* g, int B, int t_lo, int t_hi, int item_lo, int item_hi,
+                         const GeomDev* geo_override, const int32_t* items_override)
 {
     if (p->dtype != NFFTB200_F32) return -1;
     using T = float;
     using C = float2;
-    GeomDev geo = make_geom<T>(p);
+    GeomDev geo = geo_override ? *geo_override : make_geom<T>(p);
+    const int32_t* d_tile_items = items_override ? items_override : p->d_tile_items;
     const int units = geo.Nt[0] / 2;
     int bx = 32;
     const cudaStream_t st = p->stream;
@@ -862,11 +864,11 @@ int nfftb_gather_scratch(nfftb200_plan* p, const void* scratch, void* g, int B, 
         if (geo.bs[2] == 16 && geo.Nt[2] % 16 == 0 && 16 >= 2 * MT) {                                                            \
             while (bx < 128 && bx < units) bx <<= 1;                                                                             \
             dim3 gc((units + bx - 1) / bx, geo.Nt[1], geo.nb[2] * B * 2);                                                        \
-            k_gather_cols3d<T, MT, 16, false, 2><<<gc, bx, 0, st>>>((const C*)scratch, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo, PeerTab{}, 0); \
+            k_gather_cols3d<T, MT, 16, false, 2><<<gc, bx, 0, st>>>((const C*)scratch, (C*)g, d_tile_items, t_lo, t_hi, item_lo, item_hi, geo, PeerTab{}, 0); \
         } else {                                                                                                                 \
             while (bx < 256 && bx < units) bx <<= 1;                                                                             \
             dim3 gg((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);                                                            \
-            k_gather_tiles3d<T, MT><<<gg, bx, 0, st>>>((const C*)scratch, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo); \
+            k_gather_tiles3d<T, MT><<<gg, bx, 0, st>>>((const C*)scratch, (C*)g, d_tile_items, t_lo, t_hi, item_lo, item_hi, geo); \
         }                                                                                                                        \
         break;
     switch (p->m) {

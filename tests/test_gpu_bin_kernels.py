@@ -62,3 +62,25 @@ def test_lean_kernels_window_modes_and_layouts(m, pre, mode):
     adj = np.array(p.adjoint() * fh)
     assert rel(fwd, po.forward(f)) <= 1e-5 and rel(adj, po.adjoint(fh)) <= 1e-5
     assert np.array_equal(fwd, np.array(p * f)) and np.array_equal(adj, np.array(p.adjoint() * fh))   # bit-reproducible
+
+
+def test_cluster_pair_dsmem_halo_exchange():
+    """kernel_mode 13: clusters of two x-adjacent tile CTAs merge their shared halo through distributed shared memory and
+    write one 38-column block; the gather pass then runs on 32 x 16 x 16 tiles.  Same result as the default path up to
+    the summation order, and bit-reproducible."""
+    import torch
+    import nfft_jl_b200 as nb
+    from oracle import nfft_oracle as O
+    T, N, M = np.float32, (64, 40, 48), 300000          # Nt = (128, 80, 96): 8 x 5 x 6 tiles, all of them populated
+    k = O.random_nodes(M, 3, T, seed=23)
+    p = nb.plan_nfft(torch.from_numpy(np.ascontiguousarray(k.T)).cuda(), N, m=3, σ=2.0)
+    fh = O.random_complex(M, T, 3)
+    ref = np.array(p.adjoint() * fh)
+    p.set_kernel_mode(13)
+    got = np.array(p.adjoint() * fh)
+    err = np.linalg.norm(got.astype(np.complex128) - ref) / np.linalg.norm(ref.astype(np.complex128))
+    assert err <= 1e-6, err
+    assert np.array_equal(got, np.array(p.adjoint() * fh))
+    po = O.OraclePlan(k, N, m=3, sigma=2.0, blockSize=p.params.blockSize)
+    want = po.adjoint(fh)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-5
