@@ -160,6 +160,103 @@ k_spread_1d(const void* __restrict__ fhat_, void* __restrict__ g_, const T* __re
     }
 }
 
+
+// Cell-ordered form of the output-stationary spreader (round 2): the plan keeps the nodes sorted by grid cell
+// (sort.cu: cells1d_impl), so the nodes that reach a sub-block of NFFTB_G1D cells -- cells [t0 - m, t0 + len + m - 1),
+// periodic -- are at most two contiguous ranges of (xs2, perm2).  They are copied into shared memory with coalesced
+// loads (no counting sort, no shared atomics, no insertion sort, no scan of whole neighbour tiles), `off` holds the start
+// of every cell inside the staged list, and the gather loop is the one of k_spread_1d: thread u owns grid cell t0 + u.
+// [n_lo, n_hi) restricts the nodes to a rank's range under node sharding.
+template <typename T, int MT, bool CPLX>
+__global__ void __launch_bounds__(O1_THREADS)
+k_spread_1d_cells(const void* __restrict__ fhat_, void* __restrict__ g_, const T* __restrict__ xs2,
+                  const int32_t* __restrict__ perm2, const int32_t* __restrict__ cell_start, int n_lo, int n_hi,
+                  long long M, GeomDev geo, WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp, int cap)
+{
+    using C = typename Cplx<T>::type;
+    using V = typename std::conditional<CPLX, C, T>::type;
+    constexpr int L = 2 * MT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Nt = geo.Nt[0];
+    constexpr int W = NFFTB_G1D + L;                       // window cells [t0 - m, t0 + G + m) of the sub-block (+1 spare)
+    int* off = reinterpret_cast<int*>(smem_raw);           // [W + 1] start of window cell q inside the staged list
+    const size_t head = (sizeof(int) * (size_t)(W + 2) + 15) & ~(size_t)15;
+    V* s_v = reinterpret_cast<V*>(smem_raw + head);        // [cap] node values
+    T* s_t = reinterpret_cast<T*>(s_v + cap);              // [cap] frac - 1/2 (POLYNOMIAL) or frac + m - 1
+
+    const int t0 = blockIdx.x * NFFTB_G1D;                 // sub-blocks tile the whole grid (tiles are runs of cells)
+    const int len = min(NFFTB_G1D, Nt - t0);
+    const int b = blockIdx.y;
+    const V* fhat = reinterpret_cast<const V*>(fhat_) + (long long)b * M;
+    V* g = reinterpret_cast<V*>(g_) + (long long)b * geo.gsz;
+    const int nw = len + L - 1;                            // window cells that can reach this sub-block
+    // window cell q <-> grid cell (t0 - m + q) mod Nt; its nodes are [cs(c), cs(c + 1)) clipped to [n_lo, n_hi)
+    auto clip = [&](int v) { return min(max(v, n_lo), n_hi); };
+    // the window is [a0, a0 + nw) with a0 = t0 - m; split at the periodic boundary into <= 2 runs of cells
+    const int a0 = t0 - MT;
+    int run_c[2], run_n[2], nrun = 0;
+    if (a0 < 0) { run_c[nrun] = a0 + Nt; run_n[nrun] = min(-a0, nw); nrun++; if (nw > -a0) { run_c[nrun] = 0; run_n[nrun] = nw + a0; nrun++; } }
+    else if (a0 + nw > Nt) { run_c[nrun] = a0; run_n[nrun] = Nt - a0; nrun++; run_c[nrun] = 0; run_n[nrun] = a0 + nw - Nt; nrun++; }
+    else { run_c[nrun] = a0; run_n[nrun] = nw; nrun++; }
+    int base[2], cnt[2];
+    for (int r = 0; r < nrun; r++) {
+        base[r] = clip(cell_start[run_c[r]]);
+        cnt[r] = clip(cell_start[run_c[r] + run_n[r]]) - base[r];
+    }
+    const int total = cnt[0] + (nrun > 1 ? cnt[1] : 0);
+    const bool fits = total <= cap;
+    // offsets of the window cells in the staged list
+    for (int q = threadIdx.x; q <= nw; q += O1_THREADS) {
+        int r = 0, qq = q, pre = 0;
+        if (nrun > 1 && q >= run_n[0]) { r = 1; qq = q - run_n[0]; pre = cnt[0]; }
+        off[q] = pre + clip(cell_start[run_c[r] + qq]) - base[r];
+    }
+    if (fits) {
+        for (int r = 0, pre = 0; r < nrun; pre += cnt[r], r++)
+            for (int x = threadIdx.x; x < cnt[r]; x += O1_THREADS) {
+                const long long i = (long long)base[r] + x;
+                T ks;
+                const int c = node_cell<T>(xs2[i], Nt, ks);
+                const T d0 = sub_rn(ks, (T)(c - MT + 1));
+                s_t[pre + x] = (win.mode == NFFTB200_POLYNOMIAL) ? sub_rn(add_rn(sub_rn(d0, (T)MT), (T)1), (T)0.5) : d0;
+                s_v[pre + x] = fhat[perm2[i]];
+            }
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < len; u += O1_THREADS) {
+        T ax = 0, ay = 0;
+        if (fits) {
+#pragma unroll
+            for (int l = 0; l < L; l++) {
+                const int bk = u + 2 * MT - 1 - l;         // window cell whose tap l lands on grid cell t0 + u
+                for (int x = off[bk]; x < off[bk + 1]; x++) {
+                    const T t = s_t[x];
+                    T w;
+                    if (win.mode == NFFTB200_POLYNOMIAL) {
+                        constexpr int deg = L + 1;
+                        w = pp.c[l * deg + deg - 1];
+#pragma unroll
+                        for (int r = deg - 2; r >= 0; r--) w = tfma(w, t, pp.c[l * deg + r]);
+                    } else if (win.mode == NFFTB200_LINEAR) {
+                        const T idx = mul_rn(t, (T)win.lin_scale);
+                        const int ii = (int)idx;
+                        const T alpha = sub_rn(idx, (T)ii);
+                        int a1 = ii - l * win.lin_scale, a2 = a1 + 1;
+                        a1 = a1 < 0 ? -a1 : a1; a2 = a2 < 0 ? -a2 : a2;
+                        const T v1 = win.lin[a1], v2 = win.lin[a2];
+                        w = add_rn(v1, mul_rn(alpha, sub_rn(v2, v1)));
+                    } else {
+                        w = kb_exact<T>(sub_rn(t, (T)l), MT, win.b);
+                    }
+                    if constexpr (CPLX) { ax = tfma(w, s_v[x].x, ax); ay = tfma(w, s_v[x].y, ay); }
+                    else ax = tfma(w, s_v[x], ax);
+                }
+            }
+        }
+        if constexpr (CPLX) g[t0 + u] = make_c<T>(ax, ay); else g[t0 + u] = ax;
+    }
+}
+
 template <typename T, int MT, bool CPLX>
 __global__ void __launch_bounds__(256)
 k_interp_1d(const void* __restrict__ g_, void* __restrict__ fhat_, const T* __restrict__ xs,
@@ -212,6 +309,24 @@ int spread1d_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo
     return NFFTB200_OK;
 }
 
+template <typename T, int MT, bool CPLX>
+int spread1d_cells_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi, int cap)
+{
+    using C = typename Cplx<T>::type;
+    constexpr int W = NFFTB_G1D + 2 * MT;
+    const size_t vsz = CPLX ? sizeof(C) : sizeof(T);
+    const size_t smem = ((sizeof(int) * (size_t)(W + 2) + 15) & ~(size_t)15) + (sizeof(T) + vsz) * (size_t)cap + 16;
+    auto kern = k_spread_1d_cells<T, MT, CPLX>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((p->Nt[0] + NFFTB_G1D - 1) / NFFTB_G1D), B);
+    kern<<<grid, O1_THREADS, smem, p->stream>>>(fhat, g, (const T*)p->d_xs2, p->d_perm2, p->d_bin_start, p->h_tile_start[(size_t)t_lo],
+                                               p->h_tile_start[(size_t)t_hi], p->M, make_geom<T>(p), make_win<T>(p),
+                                               make_poly_param<T, MT>(p), cap);
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    return NFFTB200_OK;
+}
+
 }  // namespace
 
 // returns -1 when the 1-D kernels do not apply (then the generic kernels run)
@@ -228,6 +343,16 @@ static int spread1d_impl(nfftb200_plan* p, const void* fhat, void* g, int B, int
     const int64_t cap_max = ((int64_t)200 * 1024 - (int64_t)sizeof(int) * (2 * W + 4)) / (int64_t)(sizeof(T) + vsz + sizeof(int)) - 4;
     if (worst > cap_max) return -1;
     const int cap = (int)std::max<int64_t>(worst, 32);
+    // default: the cell-ordered form (plan-time sort by grid cell); kernel_mode 9 keeps the round-1 bucketing kernel.
+    // The window of a sub-block is the same either way, so the capacity counted at nodes! (max_neigh_1d) applies.
+    if (p->kernel_mode != 9 && p->bs[0] % NFFTB_G1D == 0 && nfftb_ensure_cells_1d(p) == NFFTB200_OK) {
+#define GOC(MM)                                                                                        \
+    case MM:                                                                                           \
+        return is_complex ? spread1d_cells_launch<T, MM, true>(p, fhat, g, B, t_lo, t_hi, cap)         \
+                          : spread1d_cells_launch<T, MM, false>(p, fhat, g, B, t_lo, t_hi, cap);
+        switch (p->m) { GOC(2) GOC(3) GOC(4) GOC(5) GOC(6) default: break; }
+#undef GOC
+    }
 #define GO(MM)                                                                                         \
     case MM:                                                                                           \
         return is_complex ? spread1d_launch<T, MM, true>(p, fhat, g, B, t_lo, t_hi, cap)               \
@@ -242,10 +367,15 @@ static int interp1d_impl(nfftb200_plan* p, const void* g, void* fhat, int B, int
     if (p->m < 2 || p->m > 6 || p->Nt[0] < 2 * p->m) return -1;
     const long long n = i_hi - i_lo;
     const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    // cell-ordered nodes (plan-time, sort.cu): neighbouring threads read neighbouring grid cells -- coalesced instead of
+    // 32 cache lines per load; the range [i_lo, i_hi) is tile aligned, so it names the same nodes in either order
+    const bool cells = p->kernel_mode != 9 && nfftb_ensure_cells_1d(p) == NFFTB200_OK;
+    const T* xs_use = (const T*)(cells ? p->d_xs2 : p->d_xs);
+    const int32_t* perm_use = cells ? p->d_perm2 : p->d_perm;
 #define GO(MM)                                                                                                   \
     case MM:                                                                                                     \
-        if (is_complex) k_interp_1d<T, MM, true><<<blocks, 256, 0, p->stream>>>(g, fhat, (const T*)p->d_xs, p->d_perm, i_lo, i_hi, p->M, make_geom<T>(p), make_win<T>(p), make_poly_param<T, MM>(p), B); \
-        else k_interp_1d<T, MM, false><<<blocks, 256, 0, p->stream>>>(g, fhat, (const T*)p->d_xs, p->d_perm, i_lo, i_hi, p->M, make_geom<T>(p), make_win<T>(p), make_poly_param<T, MM>(p), B); \
+        if (is_complex) k_interp_1d<T, MM, true><<<blocks, 256, 0, p->stream>>>(g, fhat, xs_use, perm_use, i_lo, i_hi, p->M, make_geom<T>(p), make_win<T>(p), make_poly_param<T, MM>(p), B); \
+        else k_interp_1d<T, MM, false><<<blocks, 256, 0, p->stream>>>(g, fhat, xs_use, perm_use, i_lo, i_hi, p->M, make_geom<T>(p), make_win<T>(p), make_poly_param<T, MM>(p), B); \
         break;
     switch (p->m) { GO(2) GO(3) GO(4) GO(5) GO(6) default: return -1; }
 #undef GO

@@ -228,11 +228,13 @@ __global__ void k_count_neigh_1d(const T* __restrict__ xs, long long M, GeomDev 
         const int t = cell / bs;
         return t * S + (cell - t * bs) / NFFTB_G1D;
     };
-    const int b0 = block_of(c);
-    atomicAdd(&cnt[b0], 1);
-    const int bl = block_of(c - (m - 1)), bh = block_of(c + m);   // blocks whose cells this node's taps reach
-    if (bl != b0) atomicAdd(&cnt[bl], 1);
-    if (bh != b0 && bh != bl) atomicAdd(&cnt[bh], 1);
+    // every sub-block whose cells the node's 2m taps reach (cells c - m + 1 .. c + m, periodic) buckets the node; a
+    // short trailing sub-block can make that three blocks, so walk the tap span instead of testing its two ends
+    int last = -1, first = -1;
+    for (int d = -(m - 1); d <= m; d++) {
+        const int bk = block_of(c + d);
+        if (bk != last && bk != first) { atomicAdd(&cnt[bk], 1); if (first < 0) first = bk; last = bk; }
+    }
     (void)nb;
 }
 __global__ void k_max_int(const int* __restrict__ a, long long n, int* __restrict__ out)
@@ -472,7 +474,104 @@ template <typename T> int bins_impl(nfftb200_plan* p, int W, int G)
     return NFFTB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 1-D: cell order.  The tile-sorted node list is sorted once more, stably, by grid cell (a global LSD radix sort on
+// the cell index: cells of a tile are contiguous, so the result is still tile-major and tile_start stays valid).
+// The 1-D kernels then see the nodes of any run of cells as ONE contiguous range: the interpolator's grid reads and
+// the spreader's staging become coalesced, and the spreader needs no per-CTA bucketing at all.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_cell_keys_1d(const T* __restrict__ xs, long long M, int Nt, uint32_t* __restrict__ keys)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    T ks;
+    keys[i] = (uint32_t)node_cell<T>(xs[i], Nt, ks);
+}
+
+template <typename T>
+__global__ void k_gather_sorted_1d(const T* __restrict__ xs, const int32_t* __restrict__ perm, const int32_t* __restrict__ order,
+                                   long long M, T* __restrict__ xs2, int32_t* __restrict__ perm2)
+{
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= M) return;
+    const int32_t i = order[q];
+    xs2[q] = xs[i];
+    perm2[q] = perm[i];
+}
+
+template <typename T> int cells1d_impl(nfftb200_plan* p)
+{
+    if (p->D != 1) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "cell order: 1-D plans only");
+    if (p->have_bins && p->bins_nq == -1) return NFFTB200_OK;
+    const int64_t M = std::max<int64_t>(p->M, 1);
+    if (M > p->cap_bins_nodes) {
+        if (p->d_xs2) cudaFree(p->d_xs2);
+        if (p->d_perm2) cudaFree(p->d_perm2);
+        p->d_xs2 = nullptr; p->d_perm2 = nullptr; p->cap_bins_nodes = 0;
+        CUDA_TRY(p, cudaMalloc(&p->d_xs2, (size_t)M * 3 * sizeof(T)));
+        CUDA_TRY(p, cudaMalloc((void**)&p->d_perm2, (size_t)M * 4));
+        p->cap_bins_nodes = M;
+    }
+    const int64_t tab = p->Nt[0] + 1;
+    if (tab > p->cap_bin_tab) {
+        if (p->d_bin_start) cudaFree(p->d_bin_start);
+        p->d_bin_start = nullptr; p->cap_bin_tab = 0;
+        CUDA_TRY(p, cudaMalloc((void**)&p->d_bin_start, (size_t)tab * 4));
+        p->cap_bin_tab = tab;
+    }
+    cudaStream_t s = p->stream;
+    if (p->M > 0) {
+        // scratch for the second sort: key / value ping-pong buffers, freed again (plan-time only)
+        uint32_t* k2[2] = {nullptr, nullptr};
+        int32_t* v2[2] = {nullptr, nullptr};
+        for (int i = 0; i < 2; i++) {
+            if (cudaMalloc((void**)&k2[i], (size_t)M * 4) != cudaSuccess || cudaMalloc((void**)&v2[i], (size_t)M * 4) != cudaSuccess) {
+                cudaGetLastError();
+                for (int j = 0; j < 2; j++) { if (k2[j]) cudaFree(k2[j]); if (v2[j]) cudaFree(v2[j]); }
+                return nfftb_fail(p, NFFTB200_OOM, "cell order: out of device memory");
+            }
+        }
+        k_cell_keys_1d<T><<<(unsigned)((p->M + 255) / 256), 256, 0, s>>>((const T*)p->d_xs, p->M, (int)p->Nt[0], k2[0]);
+        int bits = 0;
+        while ((1ll << bits) < p->Nt[0]) bits++;
+        const int passes = (bits + 7) / 8;
+        const int nCTA = (int)((p->M + SORT_TILE - 1) / SORT_TILE);
+        int cur = 0;
+        for (int ps = 0; ps < passes; ps++) {
+            const int shift = 8 * ps;
+            k_radix_hist<<<nCTA, SORT_THREADS, 0, s>>>(k2[cur], p->M, shift, p->d_hist, nCTA);
+            const long long hn = 256ll * nCTA;
+            const int nchunks = (int)((hn + SCAN_CHUNK - 1) / SCAN_CHUNK);
+            uint32_t* sums = p->d_hist + hn;
+            k_scan_chunks<<<nchunks, 1024, 0, s>>>(p->d_hist, hn, sums);
+            k_scan_sums<<<1, 1024, 0, s>>>(sums, nchunks);
+            k_scan_add<<<nchunks, 1024, 0, s>>>(p->d_hist, hn, sums);
+            k_radix_scatter<<<nCTA, SORT_THREADS, 0, s>>>(k2[cur], ps == 0 ? nullptr : v2[cur], k2[cur ^ 1], v2[cur ^ 1], p->M, shift, p->d_hist, nCTA);
+            p->launches += 5;
+            cur ^= 1;
+        }
+        if (passes == 0) { k_iota<<<(unsigned)((p->M + 255) / 256), 256, 0, s>>>(v2[cur], p->M); }
+        k_gather_sorted_1d<T><<<(unsigned)((p->M + 255) / 256), 256, 0, s>>>((const T*)p->d_xs, p->d_perm, v2[cur], p->M, (T*)p->d_xs2, p->d_perm2);
+        k_tile_start<<<(unsigned)((p->M + 1 + 255) / 256), 256, 0, s>>>(k2[cur], p->M, p->Nt[0], p->d_bin_start);
+        p->launches += 3;
+        CUDA_TRY(p, cudaStreamSynchronize(s));
+        for (int i = 0; i < 2; i++) { cudaFree(k2[i]); cudaFree(v2[i]); }
+    } else {
+        CUDA_TRY(p, cudaMemsetAsync(p->d_bin_start, 0, (size_t)tab * 4, s));
+    }
+    CUDA_TRY(p, cudaGetLastError());
+    p->have_bins = true;
+    p->bins_nq = -1;                  // marks the 1-D cell order
+    return NFFTB200_OK;
+}
+
 }  // namespace
+
+int nfftb_ensure_cells_1d(nfftb200_plan* p)
+{
+    return p->dtype == NFFTB200_F32 ? cells1d_impl<float>(p) : cells1d_impl<double>(p);
+}
 
 int nfftb_ensure_bins(nfftb200_plan* p, int W, int G)
 {

@@ -6,7 +6,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "rege
 rows = list(csv.reader(io.StringIO(out)))
 hdr = next(r for r in rows if r and r[0] == "Address")
 ia, isrc = hdr.index("Instructions Executed"), hdr.index("Source")
-iw = hdr.index("L1 Wavefronts Shared")
+iw = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else 0
 tot = 0; by = collections.Counter(); wf = 0
 for r in rows:
     if len(r) <= ia or not r[ia].isdigit(): continue
