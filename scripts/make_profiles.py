@@ -34,7 +34,12 @@ with open(os.path.join(out, f"{tag}_kernels.csv"), "w", newline="") as fh:
         import re
         short = re.search(r"(k_[a-z0-9_]+)", name).group(1)
         traffic[short] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-if "k_spread_sub3d" in traffic or "k_spread_bin3d" in traffic:
+if "k_spread_lean" in traffic:          # round 2 default kernels: same keys bench.py reads
+    tj = {"source": f"{os.path.basename(rep)} (ncu --set full, {tag}; profiles/{tag}_kernels.csv)",
+          "spread_stage_dram_bytes_per_launch": {"lean": traffic["k_spread_lean"] + traffic.get("k_gather_cols3d", 0), "sub": 828784896.0, "bin": None},
+          "per_kernel_dram_bytes_per_launch": traffic}
+    json.dump(tj, open(os.path.join(out, "ncu_traffic.json"), "w"), indent=1)
+elif "k_spread_sub3d" in traffic or "k_spread_bin3d" in traffic:
     tj = {"source": os.path.basename(rep), "per_kernel_dram_bytes_per_launch": traffic,
           "spread_dram_bytes_per_launch": traffic.get("k_spread_sub3d", 0) + traffic.get("k_gather_tiles3d", 0) + traffic.get("k_gather_cols3d", 0)}
     if "k_spread_bin3d" in traffic:      # kernel_mode 7 (bench.py --kernel-mode 7 reads this key)
