@@ -206,6 +206,15 @@ extern "C" int nfftb200_partition_tiles(const int64_t* tile_start, int64_t ntile
     return NFFTB200_OK;
 }
 
+// nfftb200_set_stream: the slab FFT plans follow the plan's stream
+void nfftb_comm_set_stream(nfftb200_plan* p)
+{
+    CommState* c = cs(p);
+    if (!c) return;
+    if (c->have_local) cufftSetStream(c->fft_local, p->stream);
+    if (c->have_last) cufftSetStream(c->fft_last, p->stream);
+}
+
 void nfftb_comm_destroy(nfftb200_plan* p)
 {
     CommState* c = cs(p);

@@ -10,6 +10,7 @@
 int nfftb_comm_exec_adjoint(nfftb200_plan* p, const void* d_fhat, void* d_f);   // comm.cu
 int nfftb_comm_exec_forward(nfftb200_plan* p, const void* d_f, void* d_fhat);
 void nfftb_comm_destroy(nfftb200_plan* p);
+void nfftb_comm_set_stream(nfftb200_plan* p);
 
 static thread_local std::string g_last_error;
 
@@ -357,6 +358,11 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
         p->fsz *= p->N[d];
     }
     if (p->ntiles >= ((int64_t)1 << 31)) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "too many tiles"); }
+    // the batch rides on gridDim.y / gridDim.z (limit 65535) in the deconvolve, gather and tile kernels
+    if ((int64_t)ntransforms > 65535 || (D == 3 && p->Nt[2] * (int64_t)ntransforms > 65535)) {
+        delete p;
+        return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "ntransforms too large for one plan (grid dimension limit 65535): split the batch");
+    }
     nfftb_build_tables(p);
     if (device < 0) {   // host-only plan (parameters + tables, for CPU-side checks); every exec call fails
         *out = p;
@@ -749,6 +755,8 @@ int nfftb200_set_stream(nfftb200_plan* p, void* cuda_stream)
     p->stream = (cudaStream_t)cuda_stream;
     CUFFT_TRY(p, cufftSetStream(p->fft, p->stream));
     if (p->have_pruned) { CUFFT_TRY(p, cufftSetStream(p->fft_xy, p->stream)); CUFFT_TRY(p, cufftSetStream(p->fft_z, p->stream)); }
+    if (p->have_fft_img) CUFFT_TRY(p, cufftSetStream(p->fft_img, p->stream));
+    nfftb_comm_set_stream(p);
     return NFFTB200_OK;
 }
 

@@ -261,8 +261,10 @@ class B200NFFTPlan:
                                  precompute=PrecomputeFlags(int(precompute)), sortNodes=bool(sortNodes),
                                  storeDeconvolutionIdx=bool(storeDeconvolutionIdx), blocking=bool(blocking),
                                  blockSize=tuple(bso))
-        if stream == "current" and torch is not None and torch.cuda.is_available():
-            self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._follow_torch_stream = stream == "current" and torch is not None and torch.cuda.is_available()
+        self._bound_stream = None
+        self._user_dims = dims
+        self._rebind_stream()
         self._timing_on = False
         self._async_keep = []
         self.J = 0
@@ -299,9 +301,11 @@ class B200NFFTPlan:
         re-entrant.  (Sharded plans are collective objects and cannot be copied.)"""
         if self.shard is not None:
             raise ArgumentError("a sharded plan cannot be copied")
-        q = B200NFFTPlan(self.k, self.N, m=self._requested[0], σ=self._requested[1], window=self.params.window,
-                         precompute=self.params.precompute, blockSize=self.params.blockSize,
-                         ntransforms=self.ntransforms, device=self.device, sortNodes=False,
+        directional = self._user_dims is not None and tuple(self._user_N) != tuple(self.N)
+        q = B200NFFTPlan(self.k, self._user_N if directional else self.N, m=self._requested[0], σ=self._requested[1],
+                         window=self.params.window, precompute=self.params.precompute, blockSize=self.params.blockSize,
+                         ntransforms=1 if directional else self.ntransforms, dims=self._user_dims if directional else None,
+                         device=self.device, sortNodes=False,
                          storeDeconvolutionIdx=self.params.storeDeconvolutionIdx, blocking=self.params.blocking)
         q.params = dataclasses.replace(self.params)
         return q
@@ -349,6 +353,23 @@ class B200NFFTPlan:
 
     def set_stream(self, cuda_stream: int):
         _check(self._h, self._L.nfftb200_set_stream(self._h, C.c_void_p(cuda_stream)))
+        self._bound_stream = cuda_stream
+        if not getattr(self, "_in_rebind", False):
+            self._follow_torch_stream = False          # an explicit stream: stop following torch's current stream
+
+    def _rebind_stream(self):
+        """stream="current" plans follow torch's CURRENT stream: it is looked up again at every call and the plan is
+        re-bound when it changed (nfftb200_set_stream synchronises the old stream first), so tensors produced on the
+        caller's stream are never consumed on a stale one"""
+        if not self._follow_torch_stream:
+            return
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        if cur != self._bound_stream:
+            self._in_rebind = True
+            try:
+                self.set_stream(cur)
+            finally:
+                self._in_rebind = False
 
     def sync(self):
         _check(self._h, self._L.nfftb200_sync(self._h))
@@ -374,6 +395,7 @@ class B200NFFTPlan:
 
     # ---- nodes!(p, k)  src/implementation.jl:108-141 --------------------------------------------
     def nodes_(self, k):
+        self._rebind_stream()
         D = self.D
         if _is_torch(k) and k.is_cuda:
             kk = k if k.dim() == 2 else k.reshape(1, -1)
@@ -498,6 +520,7 @@ class B200NFFTPlan:
             buf.copied_from[...] = buf.keep
 
     def _timing(self, timing):
+        self._rebind_stream()
         on = timing is not None or self._timing_on
         if on != self._timing_on:
             self._L.nfftb200_set_timing(self._h, int(on))
@@ -585,6 +608,7 @@ class B200NFFTPlan:
         return np.iscomplexobj(x)
 
     def convolve_(self, g, fHat):
+        self._rebind_stream()
         """convolve!(p, g, fHat) -> fHat  (src/convolution.jl:20-53)"""
         if tuple(g.shape) != self.Ñ:
             raise DimensionMismatch(f"size(g)={tuple(g.shape)} ≠ Ñ = {self.Ñ}")
@@ -603,6 +627,7 @@ class B200NFFTPlan:
         return fHat
 
     def convolve_transpose_(self, fHat, g):
+        self._rebind_stream()
         """convolve_transpose!(p, fHat, g) -> g  (src/convolution.jl:115-149)"""
         if tuple(g.shape) != self.Ñ:
             raise DimensionMismatch(f"size(g)={tuple(g.shape)} ≠ Ñ = {self.Ñ}")
@@ -622,6 +647,7 @@ class B200NFFTPlan:
         return g
 
     def deconvolve_(self, f, g):
+        self._rebind_stream()
         bi = self._in(f, self.N, self.cT, "f")
         bo = self._out(g, self.Ñ, self.cT, "g")
         self._same_side(bi, bo, None)
@@ -630,6 +656,7 @@ class B200NFFTPlan:
         return g
 
     def deconvolve_transpose_(self, g, f):
+        self._rebind_stream()
         bi = self._in(g, self.Ñ, self.cT, "g")
         bo = self._out(f, self.N, self.cT, "f")
         self._same_side(bi, bo, None)
@@ -638,6 +665,7 @@ class B200NFFTPlan:
         return f
 
     def fft_(self, direction):
+        self._rebind_stream()
         _check(self._h, self._L.nfftb200_fft(self._h, int(direction)))
 
     # ---- multi-GPU -----------------------------------------------------------------------------------

@@ -684,3 +684,38 @@ def test_native_sdc_matches_operator_loop(nb, D, T):
     pb = nb.plan_nfft(k.T, N, m=4, σ=2.0, ntransforms=2)
     with pytest.raises(NotImplementedError):
         nb.sdc(pb)
+
+
+def test_plan_follows_torch_stream_and_copy_keeps_dims(nb):
+    """round-1 ADVICE: (1) a stream="current" plan re-binds to torch's current stream at every call, so work queued on a
+    side stream (inputs produced there, outputs consumed there) is ordered correctly; (2) copy() of a directional plan
+    keeps dims and the user-facing sizes; (3) a batch that would overflow the grid dimension limit fails at plan time."""
+    import copy as _copy
+    import torch
+    T = np.float32
+    N, M = (24, 20, 16), 9000
+    k = O.random_nodes(M, 3, T, seed=5)
+    kd = torch.from_numpy(np.ascontiguousarray(k.T)).cuda()
+    p = nb.plan_nfft(kd, N, m=3, σ=2.0)
+    f = torch.from_numpy(O.random_complex(N, T, 6)).cuda()
+    want = p * f
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        g = (f * 2.0)                                  # produced on the side stream ...
+        out = p.empty_out()
+        nb.mul_(out, p, g.permute(2, 1, 0).contiguous().permute(2, 1, 0))        # ... consumed by the plan on the same stream
+        got = out / 2.0
+    side.synchronize()
+    assert rel(got.cpu().numpy(), want.cpu().numpy() if hasattr(want, "cpu") else want) < 1e-6
+    # directional copy
+    N3 = (10, 8, 14)
+    k2 = O.random_nodes(300, 2, np.float64, seed=7)
+    pd = nb.plan_nfft(k2.T, N3, m=4, σ=2.0, dims=range(2, 4))
+    qd = _copy.copy(pd)
+    assert qd.size_in() == pd.size_in() and qd.size_out() == pd.size_out()
+    x = O.random_complex(N3, np.float64, 8)
+    assert np.array_equal(pd * x, qd * x)
+    # grid-dimension limit is a plan-time error, not a launch failure
+    with pytest.raises(Exception):
+        nb.plan_nfft(kd, N, m=3, σ=2.0, ntransforms=70000)
