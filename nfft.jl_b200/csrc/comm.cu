@@ -488,6 +488,7 @@ int nfftb200_comm_init(nfftb200_plan* p, const void* nccl_unique_id, int rank, i
     if (mode != NFFTB200_SHARD_NODES) return nfftb_fail(p, NFFTB200_BAD_ARGUMENT, "unknown sharding mode");
     if (p->device < 0) return nfftb_fail(p, NFFTB200_CUDA_ERROR, "host-only plan (device < 0): no CPU fallback exists");
     if (p->B != 1) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "node sharding needs ntransforms == 1");
+    if (p->D > 3) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "node sharding: only D = 1, 2, 3 are supported");
     if (p->gsz % nranks) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "grid size must be divisible by the number of ranks");
     if (!nccl_unique_id) return nfftb_fail(p, NFFTB200_BAD_ARGUMENT, "nccl_unique_id == NULL");
     if (!api().ok) return nfftb_fail(p, NFFTB200_NCCL_ERROR, "libnccl.so.2 could not be loaded");

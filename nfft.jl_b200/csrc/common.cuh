@@ -10,7 +10,7 @@
 
 #include "../../include/nfftb200.h"
 
-#define NFFTB_MAX_D 3
+#define NFFTB_MAX_D 4            // D = 4 runs on the generic kernels (test/accuracy.jl:43); the tiled kernels are 1-D / 2-D / 3-D
 #define NFFTB_MAX_M 8            // taps per dim = 2m <= 16
 #define NFFTB_G1D 256            // cells per CTA of the 1-D output-stationary spreader
 
@@ -81,10 +81,10 @@ struct nfftb200_plan {
     int precompute = NFFTB200_POLYNOMIAL;
     int B = 1;                // ntransforms
     int device = 0;
-    int64_t N[NFFTB_MAX_D] = {1, 1, 1};
-    int64_t Nt[NFFTB_MAX_D] = {1, 1, 1};
-    int64_t bs[NFFTB_MAX_D] = {1, 1, 1};
-    int64_t nb[NFFTB_MAX_D] = {1, 1, 1};
+    int64_t N[NFFTB_MAX_D] = {1, 1, 1, 1};
+    int64_t Nt[NFFTB_MAX_D] = {1, 1, 1, 1};
+    int64_t bs[NFFTB_MAX_D] = {1, 1, 1, 1};
+    int64_t nb[NFFTB_MAX_D] = {1, 1, 1, 1};
     int64_t ntiles = 1;
     int64_t gsz = 1, fsz = 1;
     int64_t lut_size = 0;
@@ -99,6 +99,8 @@ struct nfftb200_plan {
     // pruned 3-D FFT: 2-D FFTs only on the z-planes that hold image frequencies + 1-D FFT along z
     cufftHandle fft_xy = 0, fft_z = 0;
     bool have_pruned = false;
+    cufftHandle fft_d4 = 0;            // D = 4: 1-D transform along the 4th dimension (cuFFT plans have rank <= 3)
+    bool have_fft_d4 = false;
     int64_t zlo_planes = 0, zhi_planes = 0;     // planes [0, zlo) and [Nt2 - zhi, Nt2) are the non-zero ones
 
     // host copies of the tables (double), for get_table and for re-upload

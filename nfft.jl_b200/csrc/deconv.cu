@@ -38,18 +38,23 @@ k_deconv_fwd(const typename Cplx<T>::type* __restrict__ f, typename Cplx<T>::typ
     const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * VPC;
     const int u1 = blockIdx.y;
     const int u2 = blockIdx.z % geo.Nt[2];
-    const int b = blockIdx.z / geo.Nt[2];
+    const int r3 = blockIdx.z / geo.Nt[2];
+    const int u3 = r3 % geo.Nt[3];                   // Nt[3] = 1 unless D = 4
+    const int b = r3 / geo.Nt[3];
     if (u0 >= geo.Nt[0]) return;
     const int i1 = geo.D > 1 ? img_index(u1, geo.N[1], geo.Nt[1]) : 0;
-    const int i2 = geo.D > 2 ? img_index(u2, geo.N[2], geo.Nt[2]) : 0;
-    C* dst = g + (size_t)b * geo.gsz + ((size_t)u2 * geo.Nt[1] + u1) * geo.Nt[0] + u0;
+    int i2 = geo.D > 2 ? img_index(u2, geo.N[2], geo.Nt[2]) : 0;
+    const int i3 = geo.D > 3 ? img_index(u3, geo.N[3], geo.Nt[3]) : 0;
+    if (i3 < 0) i2 = -1;
+    C* dst = g + (size_t)b * geo.gsz + (((size_t)u3 * geo.Nt[2] + u2) * geo.Nt[1] + u1) * geo.Nt[0] + u0;
     C out[VPC];
 #pragma unroll
     for (int k = 0; k < VPC; k++) out[k] = make_c<T>(0, 0);
     if (i1 >= 0 && i2 >= 0) {
         const T s1 = geo.D > 1 ? lut[geo.N[0] + i1] : (T)1;
         const T s2 = geo.D > 2 ? lut[geo.N[0] + geo.N[1] + i2] : (T)1;
-        const C* src = f + (size_t)b * geo.fsz + ((size_t)i2 * geo.N[1] + i1) * geo.N[0];
+        const T s3 = geo.D > 3 ? lut[geo.N[0] + geo.N[1] + geo.N[2] + i3] : (T)1;
+        const C* src = f + (size_t)b * geo.fsz + (((size_t)i3 * geo.N[2] + i2) * geo.N[1] + i1) * geo.N[0];
 #pragma unroll
         for (int k = 0; k < VPC; k++) {
             const int i0 = img_index(u0 + k, geo.N[0], geo.Nt[0]);
@@ -59,6 +64,7 @@ k_deconv_fwd(const typename Cplx<T>::type* __restrict__ f, typename Cplx<T>::typ
                 v.x *= s0; v.y *= s0;
                 if (geo.D > 1) { v.x *= s1; v.y *= s1; }
                 if (geo.D > 2) { v.x *= s2; v.y *= s2; }
+                if (geo.D > 3) { v.x *= s3; v.y *= s3; }
                 out[k] = v;
             }
         }
@@ -78,21 +84,24 @@ k_deconv_adj(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::typ
     using C = typename Cplx<T>::type;
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i1 = blockIdx.y * blockDim.y + threadIdx.y;
-    const int i2 = blockIdx.z;
+    const int i2 = blockIdx.z % geo.N[2], i3 = blockIdx.z / geo.N[2];       // N[3] = 1 unless D = 4
     if (i0 >= geo.N[0] || i1 >= geo.N[1]) return;
     const int u0 = grid_index(i0, geo.N[0], geo.Nt[0]);
     const int u1 = geo.D > 1 ? grid_index(i1, geo.N[1], geo.Nt[1]) : 0;
     const int u2 = geo.D > 2 ? grid_index(i2, geo.N[2], geo.Nt[2]) : 0;
-    const long long gq = ((long long)u2 * geo.Nt[1] + u1) * geo.Nt[0] + u0;
-    const long long fq = ((long long)i2 * geo.N[1] + i1) * geo.N[0] + i0;
+    const int u3 = geo.D > 3 ? grid_index(i3, geo.N[3], geo.Nt[3]) : 0;
+    const long long gq = (((long long)u3 * geo.Nt[2] + u2) * geo.Nt[1] + u1) * geo.Nt[0] + u0;
+    const long long fq = (((long long)i3 * geo.N[2] + i2) * geo.N[1] + i1) * geo.N[0] + i0;
     const T s0 = lut[i0];
     const T s1 = geo.D > 1 ? lut[geo.N[0] + i1] : (T)1;
     const T s2 = geo.D > 2 ? lut[geo.N[0] + geo.N[1] + i2] : (T)1;
+    const T s3 = geo.D > 3 ? lut[geo.N[0] + geo.N[1] + geo.N[2] + i3] : (T)1;
     for (int b = 0; b < B; b++) {
         C v = g[b * geo.gsz + gq];
         v.x *= s0; v.y *= s0;
         if (geo.D > 1) { v.x *= s1; v.y *= s1; }
         if (geo.D > 2) { v.x *= s2; v.y *= s2; }
+        if (geo.D > 3) { v.x *= s3; v.y *= s3; }
         f[b * geo.fsz + fq] = v;
     }
 }
@@ -171,10 +180,10 @@ template <typename T> int deconv_impl(nfftb200_plan* p, const void* src, void* d
         const int units = (geo.Nt[0] + VPC - 1) / VPC;                      // Nt[0] is even
         int bx = 32;
         while (bx < 256 && bx < units) bx <<= 1;
-        grid = dim3((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * B);
+        grid = dim3((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * geo.Nt[3] * B);
         k_deconv_fwd<T><<<grid, bx, 0, p->stream>>>((const C*)src, (C*)dst, geo, (const T*)p->d_hat_inv);
     } else {
-        launch_dims(geo.N[0], geo.N[1], geo.N[2], grid, block);
+        launch_dims(geo.N[0], geo.N[1], geo.N[2] * geo.N[3], grid, block);
         k_deconv_adj<T><<<grid, block, 0, p->stream>>>((const C*)src, (C*)dst, geo,
                                                        (const T*)p->d_hat_inv, B);
     }

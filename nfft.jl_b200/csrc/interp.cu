@@ -43,7 +43,7 @@ k_interp_generic(const void* __restrict__ g_, void* __restrict__ fhat_, const T*
     __shared__ int s_c[8][NFFTB_MAX_D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int L = 2 * win.m, D = geo.D;
-    const int ntaps = (D == 1) ? L : (D == 2 ? L * L : L * L * L);
+    const int ntaps = (D == 1) ? L : (D == 2 ? L * L : (D == 3 ? L * L * L : L * L * L * L));
     const long long nwarps = (long long)gridDim.x * 8;
     for (long long i = i_lo + (long long)blockIdx.x * 8 + warp; i < i_hi; i += nwarps) {
         __syncwarp();
@@ -60,11 +60,12 @@ k_interp_generic(const void* __restrict__ g_, void* __restrict__ fhat_, const T*
             T ax = 0, ay = 0;
             for (int q = lane; q < ntaps; q += 32) {
                 int l0 = q % L, r = q / L;
-                int l1 = r % L, l2 = r / L;
+                int l1 = r % L, l2 = (r / L) % L, l3 = r / (L * L);
                 T w = s_w[warp][0][l0];
                 long long cell = wrap(s_c[warp][0] + l0, geo.Nt[0]);
                 if (D > 1) { w *= s_w[warp][1][l1]; cell += (long long)wrap(s_c[warp][1] + l1, geo.Nt[1]) * geo.Nt[0]; }
                 if (D > 2) { w *= s_w[warp][2][l2]; cell += (long long)wrap(s_c[warp][2] + l2, geo.Nt[2]) * geo.Nt[0] * geo.Nt[1]; }
+                if (D > 3) { w *= s_w[warp][3][l3]; cell += (long long)wrap(s_c[warp][3] + l3, geo.Nt[3]) * geo.Nt[0] * geo.Nt[1] * geo.Nt[2]; }
                 if (CPLX) {
                     const C v = ((const C*)g_)[b * geo.gsz + cell];
                     ax = tfma(w, v.x, ax); ay = tfma(w, v.y, ay);

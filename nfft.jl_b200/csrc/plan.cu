@@ -65,7 +65,7 @@ void default_tiles(nfftb200_plan* p)
 {
     const int D = p->D;
     for (int d = 0; d < D; d++) {
-        int64_t v = (D == 1) ? 1024 : (D == 2 ? 64 : 16);
+        int64_t v = (D == 1) ? 1024 : (D == 2 ? 64 : (d < 3 ? 16 : 1));      // _blockSize, src/precomputation.jl:59-77
         p->bs[d] = std::min<int64_t>(v, p->Nt[d]);
     }
     if (D == 3) {
@@ -82,13 +82,26 @@ void default_tiles(nfftb200_plan* p)
 
 int make_fft(nfftb200_plan* p)
 {
-    int n[3];
-    for (int d = 0; d < p->D; d++) n[d] = (int)p->Nt[p->D - 1 - d];   // column-major -> cuFFT row-major
     const cufftType ty = p->dtype == NFFTB200_F32 ? CUFFT_C2C : CUFFT_Z2Z;
     CUFFT_TRY(p, cufftCreate(&p->fft));
     p->have_fft = true;
     size_t ws = 0;
-    long long nn[3] = {n[0], n[1], n[2]};
+    if (p->D == 4) {
+        // cuFFT plans have rank <= 3: a batched 3-D transform over dims 1..3 of every (u4, transform) slice, then a strided
+        // 1-D transform along dim 4
+        const long long vol3 = p->Nt[0] * p->Nt[1] * p->Nt[2];
+        long long n3[3] = {p->Nt[2], p->Nt[1], p->Nt[0]};
+        CUFFT_TRY(p, cufftMakePlanMany64(p->fft, 3, n3, nullptr, 1, vol3, nullptr, 1, vol3, ty, p->Nt[3] * p->B, &ws));
+        CUFFT_TRY(p, cufftSetStream(p->fft, p->stream));
+        long long n1[1] = {p->Nt[3]}, emb[1] = {p->Nt[3]};
+        CUFFT_TRY(p, cufftCreate(&p->fft_d4));
+        p->have_fft_d4 = true;
+        CUFFT_TRY(p, cufftMakePlanMany64(p->fft_d4, 1, n1, emb, vol3, 1, emb, vol3, 1, ty, vol3, &ws));
+        CUFFT_TRY(p, cufftSetStream(p->fft_d4, p->stream));
+        return NFFTB200_OK;
+    }
+    long long nn[3] = {1, 1, 1};
+    for (int d = 0; d < p->D; d++) nn[d] = p->Nt[p->D - 1 - d];      // column-major -> cuFFT row-major
     CUFFT_TRY(p, cufftMakePlanMany64(p->fft, p->D, nn, nullptr, 1, p->gsz, nullptr, 1, p->gsz, ty, p->B, &ws));
     CUFFT_TRY(p, cufftSetStream(p->fft, p->stream));
     return NFFTB200_OK;
@@ -162,6 +175,18 @@ int run_fft(nfftb200_plan* p, void* grid, int dir, bool pruned = false)
     else
         CUFFT_TRY(p, cufftExecZ2Z(p->fft, (cufftDoubleComplex*)grid, (cufftDoubleComplex*)grid, cdir));
     p->launches++;
+    if (p->have_fft_d4) {
+        for (int b = 0; b < p->B; b++) {
+            if (p->dtype == NFFTB200_F32) {
+                cufftComplex* gb = (cufftComplex*)grid + (size_t)b * p->gsz;
+                CUFFT_TRY(p, cufftExecC2C(p->fft_d4, gb, gb, cdir));
+            } else {
+                cufftDoubleComplex* gb = (cufftDoubleComplex*)grid + (size_t)b * p->gsz;
+                CUFFT_TRY(p, cufftExecZ2Z(p->fft_d4, gb, gb, cdir));
+            }
+            p->launches++;
+        }
+    }
     return NFFTB200_OK;
 }
 
@@ -308,7 +333,7 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
 {
     if (!out) return nfftb_fail(nullptr, NFFTB200_BAD_ARGUMENT, "out == NULL");
     *out = nullptr;
-    if (D < 1 || D > NFFTB_MAX_D) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "only D = 1, 2, 3 are supported");
+    if (D < 1 || D > NFFTB_MAX_D) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "only D = 1, 2, 3, 4 are supported");
     if (dtype != NFFTB200_F32 && dtype != NFFTB200_F64) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "dtype");
     if (window < NFFTB200_KAISER_BESSEL || window > NFFTB200_COSH_TYPE)
         return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "Window not yet implemented!");
@@ -359,7 +384,7 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
     }
     if (p->ntiles >= ((int64_t)1 << 31)) { delete p; return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "too many tiles"); }
     // the batch rides on gridDim.y / gridDim.z (limit 65535) in the deconvolve, gather and tile kernels
-    if ((int64_t)ntransforms > 65535 || (D == 3 && p->Nt[2] * (int64_t)ntransforms > 65535)) {
+    if ((int64_t)ntransforms > 65535 || (D >= 3 && p->Nt[2] * p->Nt[3] * (int64_t)ntransforms > 65535)) {
         delete p;
         return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "ntransforms too large for one plan (grid dimension limit 65535): split the batch");
     }
@@ -415,6 +440,7 @@ int nfftb200_destroy(nfftb200_plan* p)
     if (p->s_down) cudaStreamDestroy(p->s_down);
     nfftb_comm_destroy(p);
     if (p->have_fft) cufftDestroy(p->fft);
+    if (p->have_fft_d4) cufftDestroy(p->fft_d4);
     if (p->have_pruned) { cufftDestroy(p->fft_xy); cufftDestroy(p->fft_z); }
     void* bufs[] = {p->d_hat_inv, p->d_poly, p->d_lin, p->d_grid, p->d_xs, p->d_tile_start, p->d_keys[0],
                     p->d_keys[1], p->d_vals[0], p->d_vals[1], p->d_hist, p->d_flag, p->d_stage_f,
@@ -756,6 +782,7 @@ int nfftb200_set_stream(nfftb200_plan* p, void* cuda_stream)
     CUFFT_TRY(p, cufftSetStream(p->fft, p->stream));
     if (p->have_pruned) { CUFFT_TRY(p, cufftSetStream(p->fft_xy, p->stream)); CUFFT_TRY(p, cufftSetStream(p->fft_z, p->stream)); }
     if (p->have_fft_img) CUFFT_TRY(p, cufftSetStream(p->fft_img, p->stream));
+    if (p->have_fft_d4) CUFFT_TRY(p, cufftSetStream(p->fft_d4, p->stream));
     nfftb_comm_set_stream(p);
     return NFFTB200_OK;
 }

@@ -131,6 +131,7 @@ int nfftb200_toeplitz_kernel(nfftb200_plan* p, void* lambda, int where)
     if (!p || !p->have_nodes) return nfftb_fail(p, NFFTB200_NO_NODES, "plan has no nodes");
     if (!lambda) return nfftb_fail(p, NFFTB200_BAD_ARGUMENT, "lambda == NULL");
     if (p->B != 1) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "Toeplitz kernel needs a plan with ntransforms = 1");
+    if (p->D > 3) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "Toeplitz kernel: only D = 1, 2, 3 are supported");
     Dev guard(p->device);
     const size_t csz = 2 * p->esz();
     // work arrays and the image-sized FFT plan live in the plan (the kernel is often rebuilt for new trajectories)
@@ -181,7 +182,7 @@ int nfftb200_toeplitz_create(nfftb200_toeplitz** out, int D, const int64_t* shap
 {
     if (!out) return tfail(nullptr, NFFTB200_BAD_ARGUMENT, "out == NULL");
     *out = nullptr;
-    if (D < 1 || D > NFFTB_MAX_D) return tfail(nullptr, NFFTB200_UNSUPPORTED, "only D = 1, 2, 3 are supported");
+    if (D < 1 || D > 3) return tfail(nullptr, NFFTB200_UNSUPPORTED, "only D = 1, 2, 3 are supported");
     if (dtype != NFFTB200_F32 && dtype != NFFTB200_F64) return tfail(nullptr, NFFTB200_UNSUPPORTED, "dtype");
     if (ntransforms < 1) return tfail(nullptr, NFFTB200_BAD_ARGUMENT, "ntransforms must be >= 1");
     if (device < 0) return tfail(nullptr, NFFTB200_CUDA_ERROR, "Toeplitz operator needs a CUDA device: no CPU fallback exists");

@@ -616,8 +616,10 @@ def ndft(k, f, chunk=2048):
             out[s:s + chunk] = np.einsum("ja,jb,ab->j", e[0], e[1], acc, optimize=True)
         elif len(N) == 3:
             out[s:s + chunk] = np.einsum("ja,jb,jc,abc->j", e[0], e[1], e[2], acc, optimize=True)
+        elif len(N) == 4:     # test/accuracy.jl:43 runs N = (6, 5, 6, 6)
+            out[s:s + chunk] = np.einsum("ja,jb,jc,jd,abcd->j", e[0], e[1], e[2], e[3], acc, optimize=True)
         else:
-            raise ValueError("D<=3")
+            raise ValueError("D<=4")
     return out
 
 
@@ -640,8 +642,10 @@ def ndft_adjoint(k, N, fHat, chunk=2048):
             out += np.einsum("j,ja,jb->ab", v, e[0], e[1], optimize=True)
         elif len(N) == 3:
             out += np.einsum("j,ja,jb,jc->abc", v, e[0], e[1], e[2], optimize=True)
+        elif len(N) == 4:
+            out += np.einsum("j,ja,jb,jc,jd->abcd", v, e[0], e[1], e[2], e[3], optimize=True)
         else:
-            raise ValueError("D<=3")
+            raise ValueError("D<=4")
     return np.asfortranarray(out)
 
 

@@ -28,7 +28,7 @@ def nb():
     return m
 
 
-SHAPES = [(255,), (31, 33), (11, 12, 14), (64, 64, 64), (256, 256), (4096,)]
+SHAPES = [(255,), (31, 33), (11, 12, 14), (64, 64, 64), (256, 256), (4096,), (6, 5, 6, 6)]
 
 
 @pytest.mark.parametrize("N", SHAPES)
@@ -61,7 +61,7 @@ def test_permutation_custom_block_size(nb, bs):
     assert np.array_equal(np.diff(ts), counts)
 
 
-@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14), (32, 32, 32)])
+@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14), (32, 32, 32), (6, 5, 6, 6)])
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("pre", [O.POLYNOMIAL, O.LINEAR, O.FULL, O.TENSOR])
 @pytest.mark.parametrize("kernel_mode", [0, 1, 2])
@@ -90,7 +90,7 @@ def test_forward_adjoint_vs_oracle(nb, N, T, pre, kernel_mode):
 WINDOW_EPS = {"kaiser_bessel": 1e-7, "cosh_type": 1e-7, "gauss": 1e-3, "kaiser_bessel_rev": 1e-6, "spline": 1e-4}
 
 
-@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14)])
+@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14), (6, 5, 6, 6)])
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("pre", [O.POLYNOMIAL, O.LINEAR, O.FULL, O.TENSOR])
 @pytest.mark.parametrize("window", ["cosh_type", "gauss", "kaiser_bessel_rev", "spline"])

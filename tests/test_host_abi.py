@@ -162,8 +162,14 @@ def test_other_window_tables_match_oracle(nb, T, wi):
 
 def test_errors_and_no_cpu_fallback(nb):
     L = nb.lib()
-    st, h = host_plan(nb, (4, 4, 4, 4), np.float64, 4, 2.0)
-    assert st == 4                                              # D = 4 unsupported
+    st, h = host_plan(nb, (4, 4, 4, 4, 4), np.float64, 4, 2.0)
+    assert st == 4                                              # D = 5 unsupported (D = 4 runs: test/accuracy.jl:43)
+    st, h = host_plan(nb, (6, 5, 6, 6), np.float64, 5, 2.0)
+    assert st == 0
+    Nt4 = (C.c_int64 * 4)(); bs4 = (C.c_int64 * 4)()
+    L.nfftb200_get_info(h, Nt4, bs4, None, None, None, None)
+    assert tuple(Nt4) == (12, 10, 12, 12) and tuple(bs4) == (12, 10, 12, 1)     # _blockSize: 16,16,16 capped by Ñ, then 1
+    L.nfftb200_destroy(h)
     st, h = host_plan(nb, (16,), np.float64, 9, 2.0)
     assert st == 4
     st, h = host_plan(nb, (16,), np.float64, 4, 2.0, pre=7)

@@ -56,11 +56,11 @@ def test_shift_and_check_nodes():
     O.check_nodes(np.array([[0.5, -0.5]]))                # closed interval is legal
 
 
-@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14)])
+@pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14), (6, 5, 6, 6)])
 @pytest.mark.parametrize("pre,blocking", [(O.LINEAR, True), (O.LINEAR, False), (O.FULL, False), (O.TENSOR, True),
                                           (O.POLYNOMIAL, True), (O.POLYNOMIAL, False)])
 def test_vs_ndft_reference_tolerance(N, pre, blocking):
-    """test/accuracy.jl:41-73: Kaiser-Bessel, m=5, sigma=2 => rel-L2 < 1e-7 for every mode, D=1..3"""
+    """test/accuracy.jl:41-73: Kaiser-Bessel, m=5, sigma=2 => rel-L2 < 1e-7 for every mode, D=1..4"""
     D, M = len(N), int(np.prod(N))
     k = O.random_nodes(M, D, np.float64, seed=1)
     p = O.OraclePlan(k, N, m=5, sigma=2.0, precompute=pre, blocking=blocking)
