@@ -59,7 +59,11 @@ enum {
     NFFTB200_GAUSS = 1,
     NFFTB200_SPLINE = 2,
     NFFTB200_KAISER_BESSEL_REV = 3,
-    NFFTB200_COSH_TYPE = 4
+    NFFTB200_COSH_TYPE = 4,
+    /* not in the reference: the "exponential of semicircle" window exp(beta (sqrt(1 - (x/m)^2) - 1)), beta =
+     * 0.97 pi 2m (1 - 1/(2 sigma)), evaluated on the fly in FULL mode; its Fourier coefficients have no closed form and
+     * are computed by Gauss-Legendre quadrature at plan time */
+    NFFTB200_EXP_SQRT = 5
 };
 
 /* where caller buffers live.  NFFTB200_HOST calls return when the result is in the caller's buffer.

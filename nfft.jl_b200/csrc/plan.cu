@@ -335,7 +335,7 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
     *out = nullptr;
     if (D < 1 || D > NFFTB_MAX_D) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "only D = 1, 2, 3, 4 are supported");
     if (dtype != NFFTB200_F32 && dtype != NFFTB200_F64) return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "dtype");
-    if (window < NFFTB200_KAISER_BESSEL || window > NFFTB200_COSH_TYPE)
+    if (window < NFFTB200_KAISER_BESSEL || window > NFFTB200_EXP_SQRT)
         return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "Window not yet implemented!");
     if (precompute < NFFTB200_FULL || precompute > NFFTB200_POLYNOMIAL)
         return nfftb_fail(nullptr, NFFTB200_UNSUPPORTED, "precompute flag not supported");
@@ -366,6 +366,10 @@ int nfftb200_plan_create(nfftb200_plan** out, int D, const int64_t* N, int dtype
         p->sigma = (double)p->Nt[0] / (double)p->N[0];
         p->b = M_PI * (2.0 - 1.0 / p->sigma);
         p->beta = M_PI * (double)m * (2.0 - 1.0 / p->sigma);
+    }
+    if (window == NFFTB200_EXP_SQRT) {       // exp-sqrt shape parameter (same expression in T as the device sees it)
+        if (dtype == NFFTB200_F32) p->beta = (double)(0.97f * (float)M_PI * (float)(2 * m) * (1.0f - 0.5f / (float)p->sigma));
+        else p->beta = 0.97 * M_PI * (double)(2 * m) * (1.0 - 0.5 / p->sigma);
     }
     if (block_size) {
         for (int d = 0; d < D; d++) {

@@ -56,6 +56,10 @@ double window_eval(const nfftb200_plan* p, double x)
         const double q = x / m;
         return 0.5 / m * std::cyl_bessel_i(0.0, m * p->b * std::sqrt(1.0 - q * q));
     }
+    case NFFTB200_EXP_SQRT: {
+        const double q = x / m;
+        return std::exp(p->beta * (std::sqrt(1.0 - q * q) - 1.0));
+    }
     default: {   // NFFTB200_COSH_TYPE
         const double beta = M_PI * m * (2.0 - 1.0 / p->sigma);
         const double q = x / m;
@@ -65,10 +69,39 @@ double window_eval(const nfftb200_plan* p, double x)
     }
 }
 
+// Gauss-Legendre nodes / weights on [-1, 1] (Newton on the Legendre recurrence)
+void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w)
+{
+    x.assign(n, 0.0); w.assign(n, 0.0);
+    for (int i = 0; i < n; i++) {
+        double z = std::cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1.0;
+        for (int it = 0; it < 100; it++) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 0; j < n; j++) { const double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0); }
+            pp = n * (z * p1 - p2) / (z * z - 1.0);
+            const double dz = p1 / pp;
+            z -= dz;
+            if (std::fabs(dz) < 1e-15) break;
+        }
+        x[i] = z; w[i] = 2.0 / ((1.0 - z * z) * pp * pp);
+    }
+}
+
 double window_hat_eval(const nfftb200_plan* p, double n, double Nt)
 {
     const int m = p->m;
     switch (p->window) {
+    case NFFTB200_EXP_SQRT: {
+        // phi_hat(n) = int_{-m}^{m} phi(x) cos(2 pi n x / Nt) dx, no closed form: 96-point Gauss-Legendre on [0, m]
+        static std::vector<double> gx, gw;
+        if (gx.empty()) gauss_legendre(96, gx, gw);
+        double s = 0.0;
+        for (size_t i = 0; i < gx.size(); i++) {
+            const double x = 0.5 * m * (gx[i] + 1.0), q = x / m;
+            s += gw[i] * std::exp(p->beta * (std::sqrt(1.0 - q * q) - 1.0)) * std::cos(2.0 * M_PI * n * x / Nt);
+        }
+        return s * m;      // 2 * (m / 2) * sum
+    }
     case NFFTB200_KAISER_BESSEL:
         return kb_window_hat(n, Nt, m, p->b);
     case NFFTB200_GAUSS: {

@@ -75,6 +75,10 @@ template <typename T> __device__ __noinline__ T win_other(T x, int m, const WinD
         const T q = x / mm;
         return (T)0.5 / mm * ti0(mm * w.b * tsqrt((T)1 - q * q));
     }
+    if (w.window == NFFTB200_EXP_SQRT) {
+        const T q = x / mm;
+        return texp(w.beta * (tsqrt((T)1 - q * q) - (T)1));
+    }
     if (w.window == NFFTB200_COSH_TYPE) {
         const T q = x / mm;
         const T alpha = tsqrt((T)1 - q * q);

@@ -81,7 +81,7 @@ mutable struct B200NFFTPlan{T,D,DIM,AT<:AbstractArray} <: AbstractNFFTPlan{T,DIM
 end
 
 # order of the NFFTB200_* window enum in include/nfftb200.h
-const WINDOWS = (:kaiser_bessel, :gauss, :spline, :kaiser_bessel_rev, :cosh_type)
+const WINDOWS = (:kaiser_bessel, :gauss, :spline, :kaiser_bessel_rev, :cosh_type, :exp_sqrt)   # :exp_sqrt is not in the reference
 
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float64}) = Cint(1)

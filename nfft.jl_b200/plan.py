@@ -42,7 +42,7 @@ class DimensionMismatch(ValueError):
 
 
 # getWindow symbols (src/windowFunctions.jl:4-19) in the order of the NFFTB200_* window enum
-WINDOWS = ("kaiser_bessel", "gauss", "spline", "kaiser_bessel_rev", "cosh_type")
+WINDOWS = ("kaiser_bessel", "gauss", "spline", "kaiser_bessel_rev", "cosh_type", "exp_sqrt")   # exp_sqrt: not in the reference
 
 
 class PrecomputeFlags(enum.IntEnum):

@@ -146,7 +146,7 @@ def window_kaiser_bessel_hat(n, Nt, m, b):
 # --------------------------------------------------------------------------------------
 # the other window pairs (src/windowFunctions.jl:41-134), all in *grid units* x = N-tilde*k
 # --------------------------------------------------------------------------------------
-WINDOWS = ("kaiser_bessel", "gauss", "spline", "kaiser_bessel_rev", "cosh_type")
+WINDOWS = ("kaiser_bessel", "gauss", "spline", "kaiser_bessel_rev", "cosh_type", "exp_sqrt")
 
 
 def window_kaiser_bessel_rev(x, m, b, dtype=np.float64):
@@ -234,6 +234,30 @@ def window_cosh_type_hat(n, Nt, m, sigma):
     return zeta * np.where(a < gamma, lo, np.where(a > gamma, hi, eq))
 
 
+def exp_sqrt_beta(m, sigma, dtype=np.float64):
+    """shape parameter of the exp-sqrt ("exponential of semicircle") window; NOT a reference window: the north_star's
+    on-the-fly option, beta = 0.97 pi 2m (1 - 1/(2 sigma))"""
+    return dtype(0.97) * dtype(np.pi) * dtype(2 * m) * (dtype(1) - dtype(0.5) / dtype(sigma))
+
+
+def window_exp_sqrt(x, m, sigma, dtype=np.float64):
+    x = np.asarray(x, dtype=dtype)
+    beta = exp_sqrt_beta(m, sigma, dtype)
+    inside = np.abs(x) < dtype(m)
+    a = np.sqrt(np.where(inside, dtype(1) - (x / dtype(m)) ** 2, dtype(1)))
+    return np.where(inside, np.exp(beta * (a - dtype(1))), dtype(0)).astype(dtype)
+
+
+def window_exp_sqrt_hat(n, Nt, m, sigma, beta=None):
+    """phi_hat(n) = int_{-m}^{m} phi(x) cos(2 pi n x / Nt) dx by Gauss-Legendre quadrature (no closed form)"""
+    n = np.atleast_1d(np.asarray(n, dtype=np.float64))
+    gx, gw = np.polynomial.legendre.leggauss(96)
+    x = 0.5 * m * (gx + 1.0)
+    beta = float(exp_sqrt_beta(m, sigma)) if beta is None else float(beta)
+    phi = np.exp(beta * (np.sqrt(1.0 - (x / m) ** 2) - 1.0))
+    return m * (np.cos(2.0 * np.pi * np.outer(n, x) / Nt) * (gw * phi)).sum(axis=1)
+
+
 def window_eval(p: "Params", x, dtype=np.float64):
     """getWindow(window)[1] evaluated in grid units (src/windowFunctions.jl:4-19)."""
     w = p.window
@@ -247,6 +271,8 @@ def window_eval(p: "Params", x, dtype=np.float64):
         return window_spline(x, p.m, dtype)
     if w == "cosh_type":
         return window_cosh_type(x, p.m, p.sigma, dtype)
+    if w == "exp_sqrt":
+        return window_exp_sqrt(x, p.m, p.sigma, dtype)
     raise ValueError("Window %s not yet implemented!" % w)
 
 
@@ -263,6 +289,9 @@ def window_hat_eval(p: "Params", n, Nt):
         return window_spline_hat(n, Nt, p.m)
     if w == "cosh_type":
         return window_cosh_type_hat(n, Nt, p.m, p.sigma)
+    if w == "exp_sqrt":
+        beta = float(exp_sqrt_beta(p.m, p.T(p.sigma), p.T)) if p.T == np.float32 else None   # the Float32 plan's beta, as the device has it
+        return window_exp_sqrt_hat(n, Nt, p.m, p.sigma, beta).reshape(np.shape(n))
     raise ValueError("Window %s not yet implemented!" % w)
 
 

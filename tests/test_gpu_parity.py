@@ -87,13 +87,14 @@ def test_forward_adjoint_vs_oracle(nb, N, T, pre, kernel_mode):
         assert rel(out_fwd, O.ndft(k, f)) < 1e-7
 
 
-WINDOW_EPS = {"kaiser_bessel": 1e-7, "cosh_type": 1e-7, "gauss": 1e-3, "kaiser_bessel_rev": 1e-6, "spline": 1e-4}
+WINDOW_EPS = {"kaiser_bessel": 1e-7, "cosh_type": 1e-7, "gauss": 1e-3, "kaiser_bessel_rev": 1e-6, "spline": 1e-4,
+              "exp_sqrt": 1e-7}      # exp_sqrt: the north_star's on-the-fly option, not a reference window
 
 
 @pytest.mark.parametrize("N", [(255,), (31, 33), (11, 12, 14), (6, 5, 6, 6)])
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("pre", [O.POLYNOMIAL, O.LINEAR, O.FULL, O.TENSOR])
-@pytest.mark.parametrize("window", ["cosh_type", "gauss", "kaiser_bessel_rev", "spline"])
+@pytest.mark.parametrize("window", ["cosh_type", "gauss", "kaiser_bessel_rev", "spline", "exp_sqrt"])
 def test_other_windows_vs_oracle(nb, N, T, pre, window):
     """the window x precompute matrix of test/accuracy.jl:41-73 (windows of src/windowFunctions.jl:41-134):
     matched-mode parity with the oracle and the reference's per-window tolerance versus the NDFT"""

@@ -137,7 +137,7 @@ def test_tables_match_oracle(nb, T, m):
 
 
 @pytest.mark.parametrize("T", [np.float64, np.float32])
-@pytest.mark.parametrize("wi", [1, 2, 3, 4])
+@pytest.mark.parametrize("wi", [1, 2, 3, 4, 5])
 def test_other_window_tables_match_oracle(nb, T, wi):
     """getWindow pairs other than :kaiser_bessel (src/windowFunctions.jl:41-134) through the same three tables"""
     N, m = (40, 37), 5
@@ -176,7 +176,7 @@ def test_errors_and_no_cpu_fallback(nb):
     assert st == 4
     h2 = C.c_void_p()
     N1 = (C.c_int64 * 1)(16)
-    assert L.nfftb200_plan_create(C.byref(h2), 1, N1, 1, 4, 2.0, 5, 4, 1, None, -1) == 4   # unknown window
+    assert L.nfftb200_plan_create(C.byref(h2), 1, N1, 1, 4, 2.0, 6, 4, 1, None, -1) == 4   # unknown window (0..5 exist)
     st, h = host_plan(nb, (16, 16), np.float32, 4, 2.0)
     assert st == 0
     k = np.zeros((2, 8), dtype=np.float32)
