@@ -124,6 +124,10 @@ struct nfftb200_plan {
     // work items: a tile with more than item_cap nodes is split (after the sort) into several items, each a
     // (tile, node range) triple processed by its own CTA; d_tile_items[t]..[t+1] are tile t's items
     int32_t* d_items = nullptr;      // 3 * nitems: tile, n_lo, n_hi
+    int32_t* d_item_stride = nullptr;// nitems: 1 = the item is the contiguous node range [n_lo, n_hi); s > 1 (2-D plans) = it takes
+                                     // every s-th node n_lo, n_lo + s, ... < n_hi, so that the items of a crowded tile each
+                                     // see a uniform sample of its nodes (a contiguous slice of a radial trajectory is a
+                                     // wedge that lands in a few of the spreader's warp-private sub-tiles)
     int32_t* d_tile_items = nullptr; // ntiles + 1
     std::vector<int32_t> h_tile_items;
     int64_t nitems = 0, cap_items = 0;

@@ -449,7 +449,7 @@ int nfftb200_destroy(nfftb200_plan* p)
     void* bufs[] = {p->d_hat_inv, p->d_poly, p->d_lin, p->d_grid, p->d_xs, p->d_tile_start, p->d_keys[0],
                     p->d_keys[1], p->d_vals[0], p->d_vals[1], p->d_hist, p->d_flag, p->d_stage_f,
                     p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab, p->d_tilebuf, p->d_items, p->d_tile_items,
-                    p->d_xs2, p->d_perm2, p->d_bin_start, p->d_expect, p->d_ready, p->d_pair_items};
+                    p->d_xs2, p->d_perm2, p->d_bin_start, p->d_expect, p->d_ready, p->d_pair_items, p->d_item_stride};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 4; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     for (int i = 0; i < 6; i++) if (p->evk[i]) cudaEventDestroy(p->evk[i]);
@@ -492,7 +492,7 @@ int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
     CUDA_TRY(p, cudaStreamSynchronize(p->stream));
     {   // work items (load balancing of crowded tiles, e.g. the k-space centre of radial trajectories)
         const int64_t cap = p->D == 3 ? 4096 : 2048;
-        std::vector<int32_t> items;
+        std::vector<int32_t> items, strides;
         p->h_tile_items.assign((size_t)p->ntiles + 1, 0);
         for (int64_t t = 0; t < p->ntiles; t++) {
             p->h_tile_items[(size_t)t] = (int32_t)(items.size() / 3);
@@ -501,8 +501,15 @@ int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
             const int64_t parts = (hi - lo + cap - 1) / cap;
             for (int64_t q = 0; q < parts; q++) {
                 items.push_back((int32_t)t);
-                items.push_back((int32_t)(lo + (hi - lo) * q / parts));
-                items.push_back((int32_t)(lo + (hi - lo) * (q + 1) / parts));
+                if (p->D == 2 && parts > 1) {            // strided split (see d_item_stride)
+                    items.push_back((int32_t)(lo + q));
+                    items.push_back((int32_t)hi);
+                    strides.push_back((int32_t)parts);
+                } else {
+                    items.push_back((int32_t)(lo + (hi - lo) * q / parts));
+                    items.push_back((int32_t)(lo + (hi - lo) * (q + 1) / parts));
+                    strides.push_back(1);
+                }
             }
         }
         p->h_tile_items[(size_t)p->ntiles] = (int32_t)(items.size() / 3);
@@ -510,12 +517,16 @@ int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
         if (!p->d_tile_items) CUDA_TRY(p, cudaMalloc((void**)&p->d_tile_items, sizeof(int32_t) * (size_t)(p->ntiles + 1)));
         if (p->nitems > p->cap_items) {
             if (p->d_items) cudaFree(p->d_items);
-            p->d_items = nullptr; p->cap_items = 0;
+            if (p->d_item_stride) cudaFree(p->d_item_stride);
+            p->d_items = nullptr; p->d_item_stride = nullptr; p->cap_items = 0;
             CUDA_TRY(p, cudaMalloc((void**)&p->d_items, sizeof(int32_t) * 3 * (size_t)p->nitems));
+            CUDA_TRY(p, cudaMalloc((void**)&p->d_item_stride, sizeof(int32_t) * (size_t)p->nitems));
             p->cap_items = p->nitems;
         }
-        if (p->nitems > 0)
+        if (p->nitems > 0) {
             CUDA_TRY(p, cudaMemcpyAsync(p->d_items, items.data(), sizeof(int32_t) * items.size(), cudaMemcpyHostToDevice, p->stream));
+            CUDA_TRY(p, cudaMemcpyAsync(p->d_item_stride, strides.data(), sizeof(int32_t) * strides.size(), cudaMemcpyHostToDevice, p->stream));
+        }
         CUDA_TRY(p, cudaMemcpyAsync(p->d_tile_items, p->h_tile_items.data(), sizeof(int32_t) * (size_t)(p->ntiles + 1),
                                     cudaMemcpyHostToDevice, p->stream));
     }

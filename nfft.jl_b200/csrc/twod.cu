@@ -55,6 +55,7 @@ template <typename T, int MT>
 __global__ void __launch_bounds__(T2_THREADS)
 k_spread_sub2d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>::type* __restrict__ scratch,
                const T* __restrict__ xs, const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_start,
+               const int32_t* __restrict__ item_stride,
                int tile_lo, long long M, GeomDev geo, WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp)
 {
     using C = typename Cplx<T>::type;
@@ -72,6 +73,8 @@ k_spread_sub2d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
     const int32_t* item = tile_start + 3 * (size_t)(tile_lo + blockIdx.x);     // work item (tile, node range)
     const int tile_id = item[0];
     const int n_lo = item[1], n_hi = item[2];
+    const int stride = item_stride[tile_lo + blockIdx.x];                       // node q of the item is n_lo + q * stride
+    const int n_item = (n_hi - n_lo + stride - 1) / stride;
     const int tx = tile_id % geo.nb[0], ty = tile_id / geo.nb[0];
     const int cx0 = tx * geo.bs[0], cy0 = ty * geo.bs[1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,7 +98,7 @@ k_spread_sub2d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
 
     auto process_round = [&](int cbase, int nn) {
         if (lane < nn) {
-            const long long i = (long long)cbase + mylist[lane];
+            const long long i = (long long)n_lo + (long long)(cbase + mylist[lane]) * stride;
             T ks0, ks1;
             const int c0 = node_cell<T>(xs[i * 2 + 0], geo.Nt[0], ks0);
             const int c1 = node_cell<T>(xs[i * 2 + 1], geo.Nt[1], ks1);
@@ -135,11 +138,11 @@ k_spread_sub2d(const typename Cplx<T>::type* __restrict__ fhat, typename Cplx<T>
         }
     };
 
-    for (int cbase = n_lo; cbase < n_hi; cbase += T2_CHUNK) {
-        const int nc = min(T2_CHUNK, n_hi - cbase);
+    for (int cbase = 0; cbase < n_item; cbase += T2_CHUNK) {                    // cbase: item-local index of the chunk
+        const int nc = min(T2_CHUNK, n_item - cbase);
         __syncthreads();
         for (int q = threadIdx.x; q < nc; q += T2_THREADS) {
-            const long long i = (long long)cbase + q;
+            const long long i = (long long)n_lo + (long long)(cbase + q) * stride;
             T ks;
             const int l0 = node_cell<T>(xs[i * 2 + 0], geo.Nt[0], ks) - cx0;
             const int l1 = node_cell<T>(xs[i * 2 + 1], geo.Nt[1], ks) - cy0;
@@ -263,6 +266,7 @@ template <typename T, int MT>
 __global__ void __launch_bounds__(T2_THREADS)
 k_interp_row2d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::type* __restrict__ fhat,
                const T* __restrict__ xs, const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_start,
+               const int32_t* __restrict__ item_stride,
                int tile_lo, long long M, GeomDev geo, WinDev<T> win, const __grid_constant__ PolyParam<T, MT> pp)
 {
     using C = typename Cplx<T>::type;
@@ -300,10 +304,12 @@ k_interp_row2d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
-    for (int rbase = n_lo + 32 * warp; rbase < n_hi; rbase += 32 * T2_WARPS) {
-        const int nn = min(32, n_hi - rbase);
+    const int stride = item_stride[tile_lo + blockIdx.x];                       // node q of the item is n_lo + q * stride
+    const int n_item = (n_hi - n_lo + stride - 1) / stride;
+    for (int rbase = 32 * warp; rbase < n_item; rbase += 32 * T2_WARPS) {
+        const int nn = min(32, n_item - rbase);
         if (lane < nn) {
-            const long long i = (long long)rbase + lane;
+            const long long i = (long long)n_lo + (long long)(rbase + lane) * stride;
             T ks0, ks1;
             const int c0 = node_cell<T>(xs[i * 2 + 0], geo.Nt[0], ks0);
             const int c1 = node_cell<T>(xs[i * 2 + 1], geo.Nt[1], ks1);
@@ -393,7 +399,7 @@ int spread2d_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo
     dim3 grid(item_hi - item_lo, B);
     if (item_hi > item_lo)
         kern<<<grid, T2_THREADS, smem, p->stream>>>((const C*)fhat, (C*)p->d_tilebuf, (const T*)p->d_xs, p->d_perm,
-                                                   p->d_items, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
+                                                   p->d_items, p->d_item_stride, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
     int bx = 32;
     while (bx < 256 && bx < geo.Nt[0]) bx <<= 1;
     dim3 gg((geo.Nt[0] + bx - 1) / bx, geo.Nt[1], B);
@@ -416,7 +422,7 @@ int interp2d_launch(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo
     const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
     dim3 grid(item_hi - item_lo, B);
-    kern<<<grid, T2_THREADS, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm, p->d_items,
+    kern<<<grid, T2_THREADS, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm, p->d_items, p->d_item_stride,
                                                item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
     p->launches++;
     CUDA_TRY(p, cudaGetLastError());
