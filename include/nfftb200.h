@@ -143,9 +143,12 @@ int nfftb200_get_timing(nfftb200_plan* p, double out[7]);
 int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
 
 /* kernel-selection knob for benchmarking/tests:
- *   0 = auto: tiled shared-memory kernels where they apply (spreader stores per-tile sub-grids with TMA bulk copies
- *       and a gather pass sums them: no atomics; interpolator stages aligned interior tiles with a TMA tensor map;
- *       3-D FFT pruned to the z-planes that carry image frequencies),
+ *   0 = auto: tiled shared-memory kernels where they apply.  Float32 3-D plans with m <= 3 run the (tile, bin)-ordered
+ *       register-window kernels (csrc/spread_lean.cuh, csrc/interp_lean.cuh: no floating-point atomics, interior tiles
+ *       staged by a TMA tensor map, LINEAR table staged by a bulk TMA copy); other 3-D plans the warp-private sub-tile
+ *       spreader (per-tile sub-grids stored with TMA bulk copies) and the row-per-lane interpolator; a gather pass sums
+ *       the per-tile sub-grids; 1-D plans work on a plan-time cell order; 3-D FFT pruned to the z-planes that carry
+ *       image frequencies; D = 4 runs on the generic kernels,
  *   1 = force the generic warp-per-node kernels (global vector REDs),
  *   2 = tiled spreader with the halo flushed by vector REDs instead of scratch + gather,
  *   3 = auto, but the interpolator never uses the TMA tensor-map load,
