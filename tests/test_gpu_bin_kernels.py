@@ -84,3 +84,24 @@ def test_cluster_pair_dsmem_halo_exchange():
     po = O.OraclePlan(k, N, m=3, sigma=2.0, blockSize=p.params.blockSize)
     want = po.adjoint(fh)
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-5
+
+
+@pytest.mark.parametrize("N", [(4, 4, 4), (6, 10, 8), (16, 8, 4), (8, 8, 24), (12, 20, 9)])
+@pytest.mark.parametrize("m", [2, 3])
+def test_lean_kernels_tiny_and_ragged_grids(N, m):
+    """Float32 3-D plans on grids smaller than one tile (the padded tile wraps onto itself), with partial last tiles and
+    odd image sizes: whatever kernel the default mode picks must match the oracle"""
+    import torch
+    import nfft_jl_b200 as nb
+    from oracle import nfft_oracle as O
+    T = np.float32
+    for M in (1, 37, 5000):
+        k = O.random_nodes(M, 3, T, seed=M)
+        p = nb.plan_nfft(torch.from_numpy(np.ascontiguousarray(k.T)).cuda(), N, m=m, σ=2.0)
+        po = O.OraclePlan(k, N, m=m, sigma=2.0, blockSize=p.params.blockSize)
+        assert np.array_equal(p.permutation()[0], po.perm)
+        f = O.random_complex(N, T, 2); fh = O.random_complex(M, T, 3)
+        fwd = np.array(p * f); adj = np.array(p.adjoint() * fh)
+        wf = po.forward(f); wa = po.adjoint(fh)
+        assert np.linalg.norm(fwd - wf) <= 1e-5 * np.linalg.norm(wf), (N, m, M)
+        assert np.linalg.norm(adj - wa) <= 1e-5 * np.linalg.norm(wa), (N, m, M)
