@@ -13,6 +13,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "bin_common.cuh"
 #include "interp_bin.cuh"
 
@@ -32,8 +34,14 @@ template <int MT, int W> struct LeanGeom {
 //            are staged (the box start must be 16-byte aligned, hence the even start; tiles that wrap periodically are
 //            staged row by row with cp.async into the same layout).  A pitch of 26 cells = 13 sixteen-byte granules keeps
 //            the 8 lanes of a quarter-warp (8 consecutive y rows) on 8 distinct granules, so the window is loaded with
-//            conflict-free LDS.128: 4 per row when the window starts on an even cell, 5 otherwise.
+//            conflict-free LDS.128.  In this layout the x extent of the register window is LEAN_WIDE_WX = 10 cells starting
+//            on an EVEN slot: 5 aligned LDS.128 per row, no parity cases, and -- because 10 cells hold the 2m <= 6 taps of
+//            every node whose first tap lies in a run of 4 cells -- only TWO windows per 8-cell octant along x instead of
+//            three (the plan-time order refines every x bin by that 4-cell half, sort.cu: k_bin_order).  Measured before
+//            this form (ncu source view, C2): the 8-cell window cost 30 issue slots per node (LDS + 32 register moves
+//            that reconcile the even / odd start cases at the join) against 36 for the arithmetic itself.
 constexpr int LEAN_WIDE_PITCH = 26;
+constexpr int LEAN_WIDE_WX = 10;
 
 template <int MT, int W> struct LeanInterpLayout {
     static constexpr int RW = 4 * W;                         // record: wx[W] | wy[W] | wz[W] | window origin (3 ints), pad
@@ -89,6 +97,11 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
     constexpr int L = LG::L, G = LG::G, S3 = LG::S3, NQ = LG::NQ, RW = LeanInterpLayout<MT, W>::RW;
     constexpr int NWARP = NFFTB_BIN_WARPS, RND = NFFTB_BIN_ROUND, NP = 2;
     static_assert(RND == 8, "rounds of 8 nodes");
+    // record of a node: wx[WXR] | wy[W] | wz[W] | window origin (3 ints); WX = cells of the register window along x
+    constexpr int WX = WIDE ? LEAN_WIDE_WX : W, WXR = WIDE ? 12 : W;
+    constexpr int OY = WXR, OZ = WXR + W, OO = WXR + 2 * W;
+    static_assert(OO + 4 <= RW && (OO % 4) == 0, "record layout");
+    static_assert(!WIDE || LEAN_WIDE_WX >= L + 4, "a 10-cell window must hold the taps of 4 consecutive first-tap cells");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C* P = reinterpret_cast<C*>(smem_raw);                                          // [PZ][PL] padded tile
@@ -130,7 +143,30 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
         if (tma_tile) tma_load_4d(P, &tmap, mbar, 2 * (cx0 - MT - xs_), cy0 - MT, cz0 - MT, (int)blockIdx.y);
         if (lut_floats > 0) lean_bulk_g2s(lut, win.lin, (unsigned)(sizeof(T) * ((lut_floats + 3) & ~3)), mbar);
     }
-    if (!tma_tile) {
+    if (!tma_tile && WIDE) {
+        // all 26 slots of every row, two cells (16 bytes) per copy: slot 0 is the even cell x0 - xs_, the grid width is
+        // even, so a pair never straddles the periodic wrap.  16 lanes per row, two rows per warp pass.
+        const int x0 = cx0 - MT - xs_, y0 = cy0 - MT, z0 = cz0 - MT;
+        const bool fw = LEAN_WIDE_PITCH <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
+        const int pr = lane & 15, rsel = lane >> 4;
+        const bool onp = pr < LEAN_WIDE_PITCH / 2;
+        const int xg = wrapc(x0 + 2 * pr, geo.Nt[0], fw);
+        for (int z = 0; z < PZ; z++) {
+            unsigned gz = (unsigned)wrapc(z0 + z, geo.Nt[2], fw);
+            const C* gb = g;
+            if (PEER) {                                                     // plane gz lives on rank gz / planes
+                const unsigned owner = gz / (unsigned)slabs.planes;
+                gb = (const C*)slabs.base[owner];
+                gz -= owner * (unsigned)slabs.planes;
+            }
+            gz *= geo.Nt[1];
+            for (int y = 2 * warp + rsel; y < PY; y += 2 * NWARP) {
+                const C* src = gb + (size_t)(gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0] + xg;
+                if (onp) cp_async_pair(P + (z * PL + y * PXp + 2 * pr), src);
+            }
+        }
+    }
+    if (!tma_tile && !WIDE) {
         const int x0 = cx0 - MT, y0 = cy0 - MT, z0 = cz0 - MT;
         const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1] && PZ <= geo.Nt[2];
         const int xg0 = wrapc(x0 + lane, geo.Nt[0], fw), xg1 = wrapc(x0 + lane + 32, geo.Nt[0], fw);
@@ -146,7 +182,7 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
             gz *= geo.Nt[1];
             for (int y = warp; y < PY; y += NWARP) {
                 const C* src = gb + (size_t)(gz + wrapc(y0 + y, geo.Nt[1], fw)) * (unsigned)geo.Nt[0];
-                C* dst = P + (z * PL + y * PXp + lane + xs_);
+                C* dst = P + (z * PL + y * PXp + lane);
                 if (on0) cp_async_cell(dst, src + xg0);
                 if (on1) cp_async_cell(dst + 32, src + xg1);
             }
@@ -171,8 +207,8 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
     WinDev<T> winl = win;
     if (lut_floats > 0) winl.lin = lut;
 
-    BinRow<T, W> win_row[NP];
-    int c0 = -1, c1 = -1, c2 = -1;                                           // origin of the resident window
+    BinRow<T, WX> win_row[NP];
+    int lastwo = -1;                                                         // window origin (dimension wd) of the previous node
     for (int rbase = nl0; rbase < nl1; rbase += RND) {
         const int nn = min(RND, nl1 - rbase);
         const T x = xnext;
@@ -182,84 +218,98 @@ k_interp_lean(const float2* __restrict__ g, float2* __restrict__ fhat, const flo
             if (wn < RND && nb0 + wn < nl1) xnext = xs2[(long long)(nb0 + wn) * 3 + wd];
             if (lane < RND && nb0 + lane < nl1) jnext = perm2[nb0 + lane];
         }
+        int wo = -1;
         if (wn < nn) {                                                       // weights of (node wn of the round, dimension wd)
             T ks;
             const int c = node_cell<T>(x, wNt, ks);
             T w[L];
             eval_taps<T, MT>(winl, pp, ks, c, w);
             const int lc = c - wc0;                                          // first tap at padded coordinate lc + 1
-            const int wo = min(1 + bin_first<W, G>(bin_of<W, G>(lc)), wmax);
+            wo = min(1 + bin_first<W, G>(bin_of<W, G>(lc)), wmax);
+            int ro = wd * W, nz = W - L;                                     // row of the record, zeros around the taps
+            if (WIDE) {
+                if (wd == 0) {                                               // 10-cell window on an even slot: 4 cells of first taps
+                    const int fb = 4 * (lc >> 2) + 1;
+                    wo = fb - ((fb + xs_) & 1);
+                    nz = WXR - L;
+                } else {
+                    ro = OY + (wd - 1) * W;
+                }
+            }
             const int dl = lc + 1 - wo;                                      // first tap inside the window
-            reinterpret_cast<int*>(myrec + wn * RW + 3 * W)[wd] = wo;
-            T* rn = myrec + wn * RW + wd * W;                                // 2m taps at [dl, dl + 2m), zeros elsewhere
+            reinterpret_cast<int*>(myrec + wn * RW + OO)[wd] = wo;
+            T* rn = myrec + wn * RW + ro;                                    // 2m taps at [dl, dl + 2m), zeros elsewhere
 #pragma unroll
             for (int l = 0; l < L; l++) rn[dl + l] = w[l];
 #pragma unroll
-            for (int j = 0; j < W - L; j++) rn[j < dl ? j : j + L] = (T)0;
+            for (int j = 0; j < WXR - L; j++)
+                if (j < nz) rn[j < dl ? j : j + L] = (T)0;
+        }
+        // which nodes of the round start a new window: bit 3n + d = origin d of node n differs from its predecessor's
+        unsigned chm;
+        {
+            const int up = __shfl_up_sync(0xffffffffu, wo, 3);
+            const int pw = wn == 0 ? lastwo : up;
+            chm = __ballot_sync(0xffffffffu, wn < nn && wo != pw);
+            lastwo = __shfl_sync(0xffffffffu, wo, 3 * (nn - 1) + wd);
         }
         __syncwarp();
-        T v[2 * RND];
+        // a full round (all but the last of a warp's list) carries no per-node guards
+        auto fold_round = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            T v[2 * RND];
 #pragma unroll
-        for (int n = 0; n < RND; n++) {
-            C sn = make_float2(0.f, 0.f);
-            if (n < nn) {                                                    // warp-uniform
-                const T* rn = myrec + n * RW;
-                const int4 org = *reinterpret_cast<const int4*>(rn + 3 * W);
-                if (org.x != c0 || org.y != c1 || org.z != c2) {             // warp-uniform: first node of a bin
-                    c0 = org.x; c1 = org.y; c2 = org.z;
-                    const C* row = P + ((c2 + rowz) * PL + (c1 + rowy) * PXp + c0 + xs_);
-                    if (WIDE) {
-                        if (((c0 + xs_) & 1) == 0) {                         // warp-uniform: window starts on a 16-byte boundary
+            for (int n = 0; n < RND; n++) {
+                C sn = make_float2(0.f, 0.f);
+                if (FULL || n < nn) {                                        // warp-uniform
+                    const T* rn = myrec + n * RW;
+                    if (chm & (7u << (3 * n))) {                             // warp-uniform: first node of a window
+                        const int4 org = *reinterpret_cast<const int4*>(rn + OO);
+                        const C* row = P + ((org.z + rowz) * PL + (org.y + rowy) * PXp + org.x + xs_);
 #pragma unroll
-                            for (int p = 0; p < NP; p++) {
+                        for (int p = 0; p < NP; p++) {
+                            if (WIDE) {                                      // org.x + xs_ is even: aligned 16-byte loads
 #pragma unroll
-                                for (int k = 0; k < W / 2; k++) {
+                                for (int k = 0; k < WX / 2; k++) {
                                     const float4 u = *reinterpret_cast<const float4*>(row + p * 4 * PL + 2 * k);
                                     win_row[p].set(2 * k, make_float2(u.x, u.y)); win_row[p].set(2 * k + 1, make_float2(u.z, u.w));
                                 }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < WX; k++) win_row[p].set(k, row[p * 4 * PL + k]);
                             }
-                        } else {                                             // one cell earlier: 5 aligned loads, the ends discarded
-#pragma unroll
-                            for (int p = 0; p < NP; p++) {
-                                float4 u[W / 2 + 1];
-#pragma unroll
-                                for (int k = 0; k < W / 2 + 1; k++) u[k] = *reinterpret_cast<const float4*>(row + p * 4 * PL - 1 + 2 * k);
-#pragma unroll
-                                for (int k = 0; k < W / 2; k++) {
-                                    win_row[p].set(2 * k, make_float2(u[k].z, u[k].w)); win_row[p].set(2 * k + 1, make_float2(u[k + 1].x, u[k + 1].y));
-                                }
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int p = 0; p < NP; p++) {
-#pragma unroll
-                            for (int k = 0; k < W; k++) win_row[p].set(k, row[p * 4 * PL + k]);
                         }
                     }
-                }
-                T wx[W];
-                bin_load_row<T, W>(rn, wx);
-                const T wy = rn[W + rowy];
+                    T wx[WX];
+                    {
+                        T wl[WXR];
+                        bin_load_row<T, WXR>(rn, wl);
 #pragma unroll
-                for (int p = 0; p < NP; p++) {
-                    const T wyz = wy * rn[2 * W + rowz + 4 * p];
-                    win_row[p].dot_acc(wx, wyz, sn);
+                        for (int k = 0; k < WX; k++) wx[k] = wl[k];
+                    }
+                    const T wy = rn[OY + rowy];
+#pragma unroll
+                    for (int p = 0; p < NP; p++) {
+                        const T wyz = wy * rn[OZ + rowz + 4 * p];
+                        win_row[p].dot_acc(wx, wyz, sn);
+                    }
                 }
+                v[2 * n] = sn.x; v[2 * n + 1] = sn.y;
             }
-            v[2 * n] = sn.x; v[2 * n + 1] = sn.y;
-        }
-        int idx;
-        if (nn > RND / 2) {
-            const T tot = bin_halving_reduce<T, 2 * RND>(v, lane, idx);
-            if ((lane & (32 / (2 * RND) - 1)) == 0) myres[idx] = tot;
-        } else {
-            T h[RND];
+            int idx;
+            if (FULL || nn > RND / 2) {
+                const T tot = bin_halving_reduce<T, 2 * RND>(v, lane, idx);
+                if ((lane & (32 / (2 * RND) - 1)) == 0) myres[idx] = tot;
+            } else {
+                T h[RND];
 #pragma unroll
-            for (int k = 0; k < RND; k++) h[k] = v[k];
-            const T tot = bin_halving_reduce<T, RND>(h, lane, idx);
-            if ((lane & (32 / RND - 1)) == 0) myres[idx] = tot;
-        }
+                for (int k = 0; k < RND; k++) h[k] = v[k];
+                const T tot = bin_halving_reduce<T, RND>(h, lane, idx);
+                if ((lane & (32 / RND - 1)) == 0) myres[idx] = tot;
+            }
+        };
+        if (nn == RND) fold_round(std::true_type{});
+        else fold_round(std::false_type{});
         __syncwarp();
         if (lane < nn) fhat[jdst] = make_float2(myres[2 * lane], myres[2 * lane + 1]);
         __syncwarp();                                                        // records and results free for the next round

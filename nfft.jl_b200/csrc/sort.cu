@@ -324,7 +324,8 @@ template <typename T> int sort_impl(nfftb200_plan* p, const void* d_k)
 // (already contiguous and in ascending caller index after the radix sort) by the bin key
 //     q = octant * S^3 + colour,  octant = sum_d (b_d / S) 2^d,  colour = sum_d (b_d % S) S^d,
 // b_d = bin of the node's first tap along d (bins of G, ..., G, W-(S-1)G first-tap positions per period of W, see
-// bin_of in bin_common.cuh).  Stable (ascending caller index inside a bin) and free of data-dependent atomics: every
+// bin_of in bin_common.cuh).  Inside a bin the nodes are ordered by the 4-cell half of the period their x cell lies in, then
+// by ascending caller index (stable).  Free of data-dependent atomics: every
 // warp ranks a contiguous part of the tile with __match_any_sync, two passes (count, then place).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BINQ_MAX = 216;      // 8 * 3^3
@@ -341,32 +342,37 @@ k_bin_order(const T* __restrict__ xs, const int32_t* __restrict__ perm, const in
             GeomDev g, int W, int G, int S, int NQ, T* __restrict__ xs2, int32_t* __restrict__ perm2,
             int32_t* __restrict__ bin_start, long long ntiles)
 {
-    __shared__ int wh[8][BINQ_MAX];
-    __shared__ int tot[BINQ_MAX + 1];
+    // counters per (bin, 4-cell half of the bin period along x): the order inside a bin is by that half, which is what
+    // lets the 10-cell interpolation windows (interp_lean.cuh: LEAN_WIDE_WX) see their nodes contiguously as well
+    constexpr int NK_MAX = 2 * BINQ_MAX;
+    __shared__ int wh[8][NK_MAX];
+    __shared__ int tot[NK_MAX + 1];
+    const int NK = 2 * NQ;
     const int t = blockIdx.x;
     const int lo = tile_start[t], hi = tile_start[t + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tx = t % g.nb[0], ty = (t / g.nb[0]) % g.nb[1], tz = t / (g.nb[0] * g.nb[1]);
     const int c0[3] = {tx * g.bs[0], ty * g.bs[1], tz * g.bs[2]};
-    for (int i = threadIdx.x; i < 8 * BINQ_MAX; i += 256) (&wh[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 8 * NK_MAX; i += 256) (&wh[0][0])[i] = 0;
     __syncthreads();
     const int n = hi - lo;
     const int per_warp = ((n + 8 * 32 - 1) / (8 * 32)) * 32;          // whole groups of 32 per warp
     const int w_lo = lo + warp * per_warp, w_hi = min(hi, w_lo + per_warp);
     const unsigned lt = (1u << lane) - 1u;
     auto key_of = [&](int i) {
-        int o = 0, c = 0, sm = 1;
+        int o = 0, c = 0, sm = 1, half = 0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             T ks;
             const int cell = node_cell<T>(xs[(long long)i * 3 + d], g.Nt[d], ks);
+            if (d == 0) half = ((cell - c0[0]) >> 2) & 1;
             const int b = binq_1d(cell - c0[d], W, G, S);
             const int od = b / S;
             o += od << d;
             c += (b - od * S) * sm;
             sm *= S;
         }
-        return o * sm + c;
+        return 2 * (o * sm + c) + half;
     };
     for (int b0 = w_lo; b0 < w_hi; b0 += 32) {                         // pass 1: counts per (warp, bin)
         const int i = b0 + lane;
@@ -377,26 +383,26 @@ k_bin_order(const T* __restrict__ xs, const int32_t* __restrict__ perm, const in
         __syncwarp();
     }
     __syncthreads();
-    if (threadIdx.x < NQ) {                                            // exclusive offsets of the warps inside a bin
+    for (int k = threadIdx.x; k < NK; k += 256) {                       // exclusive offsets of the warps inside a key
         int run = 0;
-        for (int w = 0; w < 8; w++) { const int c = wh[w][threadIdx.x]; wh[w][threadIdx.x] = run; run += c; }
-        tot[threadIdx.x] = run;
+        for (int w = 0; w < 8; w++) { const int c = wh[w][k]; wh[w][k] = run; run += c; }
+        tot[k] = run;
     }
     __syncthreads();
     if (warp == 0) {                                                   // exclusive scan of the bin totals (<= 216)
-        constexpr int KPL = (BINQ_MAX + 31) / 32;
+        constexpr int KPL = (NK_MAX + 31) / 32;
         int c[KPL], sum = 0;
 #pragma unroll
-        for (int k = 0; k < KPL; k++) { const int idx = lane * KPL + k; c[k] = idx < NQ ? tot[idx] : 0; sum += c[k]; }
+        for (int k = 0; k < KPL; k++) { const int idx = lane * KPL + k; c[k] = idx < NK ? tot[idx] : 0; sum += c[k]; }
         int incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         int run = incl - sum;
 #pragma unroll
-        for (int k = 0; k < KPL; k++) { const int idx = lane * KPL + k; if (idx < NQ) tot[idx] = run; run += c[k]; }
+        for (int k = 0; k < KPL; k++) { const int idx = lane * KPL + k; if (idx < NK) tot[idx] = run; run += c[k]; }
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < NQ; q += 256) bin_start[(long long)t * NQ + q] = lo + tot[q];
+    for (int q = threadIdx.x; q < NQ; q += 256) bin_start[(long long)t * NQ + q] = lo + tot[2 * q];
     if (t == ntiles - 1 && threadIdx.x == 0) bin_start[ntiles * NQ] = hi;
     for (int b0 = w_lo; b0 < w_hi; b0 += 32) {                         // pass 2: place
         const int i = b0 + lane;

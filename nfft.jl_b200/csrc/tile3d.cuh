@@ -104,6 +104,11 @@ __device__ __forceinline__ void cp_async_cell(float2* dst, const float2* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+// two Float32 cells: both addresses 16-byte aligned
+__device__ __forceinline__ void cp_async_pair(float2* dst, const float2* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_cell(double2* dst, const double2* src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
