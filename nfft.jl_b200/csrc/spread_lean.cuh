@@ -23,13 +23,56 @@
 #define NFFTB_LEAN_EVICT_LAST 0     // 1: fused form stores its scratch tile with an L2 evict_last policy
 #endif
 
+// Which colours of warp (octant) b must be finished before warp a may read-modify-write its bin of colour c:
+//   t[(a * 8 + b) * S^3 + c] = 1 + the last colour c' < c whose bin in octant b overlaps the bin (a, c), 0 if none.
+// Bins (a, c) and (b, c') overlap iff their W-wide windows do along every dimension; the window of bin index
+// o * S + k (octant half o, colour digit k) starts at W * o + G * k.  Two bins of the same colour never overlap, every
+// wait is on an earlier colour, so the order is acyclic.  Waiting for "all warps finished all colours < c" (the first
+// form of this kernel) is the upper bound of this table; the exact table lets a warp run ahead of octants it does not
+// touch -- 15 % instead of 20 % of the warp time spent waiting in a Poisson model of C2 (scripts in DESIGN.md 3.0).
+template <int MT, int W> struct LeanNeed {
+    static constexpr int L = 2 * MT, G = W - L + 1, S = (W + G - 1) / G, S3 = S * S * S;
+    static constexpr int BYTES = (8 * 8 * S3 + 15) & ~15;
+    unsigned char t[BYTES];
+};
+template <int MT, int W> constexpr LeanNeed<MT, W> lean_make_need()
+{
+    using N = LeanNeed<MT, W>;
+    N r{};
+    for (int a = 0; a < 8; a++)
+        for (int b = 0; b < 8; b++)
+            for (int c = 0; c < N::S3; c++) {
+                int need = 0;
+                for (int e = 0; e < c && a != b; e++) {
+                    bool hit = true;
+                    int cc = c, ee = e;
+                    for (int d = 0; d < 3; d++) {
+                        const int oa = W * ((a >> d) & 1) + N::G * (cc % N::S), ob = W * ((b >> d) & 1) + N::G * (ee % N::S);
+                        cc /= N::S; ee /= N::S;
+                        const int dist = oa > ob ? oa - ob : ob - oa;
+                        if (dist >= W) hit = false;
+                    }
+                    if (hit) need = e + 1;
+                }
+                r.t[(a * 8 + b) * N::S3 + c] = (unsigned char)need;
+            }
+    return r;
+}
+__device__ const LeanNeed<2, 8> g_lean_need2 = lean_make_need<2, 8>();
+__device__ const LeanNeed<3, 8> g_lean_need3 = lean_make_need<3, 8>();
+template <int MT> __device__ __forceinline__ const unsigned char* lean_need_table()
+{
+    if constexpr (MT == 2) return g_lean_need2.t;
+    else return g_lean_need3.t;
+}
+
 template <int MT, int W> struct LeanSpreadLayout {
     static constexpr int RW = 4 * W + 4;                     // record: wx[W] | wy[W] | (wz * v)[W] re, im | window origin (3 ints)
     static bool make(const int* bs, BinGeom& bg) { return bin_make_geom<float, MT, W>(bs, bg); }
     static size_t bytes(const BinGeom& bg, int lut_floats)
     {
         return sizeof(float2) * (size_t)bg.PNs + sizeof(float) * NFFTB_BIN_WARPS * NFFTB_BIN_ROUND * RW + 64 +
-               sizeof(float) * (size_t)((lut_floats + 3) & ~3) + 16 + 16;
+               LeanNeed<MT, W>::BYTES + sizeof(float) * (size_t)((lut_floats + 3) & ~3) + 16 + 16;
     }
 };
 
@@ -81,7 +124,8 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
     C* P = reinterpret_cast<C*>(smem_raw);                                          // [PZ][PL] padded tile
     T* rec = reinterpret_cast<T*>(P + bg.PNs);                                      // [NWARP][RND][RW]
     int* done = reinterpret_cast<int*>(rec + NWARP * RND * RW);                     // [NWARP] colours finished per warp (64 bytes)
-    T* lut = reinterpret_cast<T*>(done + 16);                                       // [lut_floats, rounded up to 4]: LINEAR window table
+    unsigned char* need_s = reinterpret_cast<unsigned char*>(done + 16);            // [NWARP][NWARP][S3] colour dependencies
+    T* lut = reinterpret_cast<T*>(need_s + LeanNeed<MT, W>::BYTES);                 // [lut_floats, rounded up to 4]: LINEAR window table
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(lut + ((lut_floats + 3) & ~3));
 
     const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
@@ -128,6 +172,8 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
         const int n16 = (int)((sizeof(C) * (size_t)bg.PNs) / 16);
         for (int q = threadIdx.x; q < n16; q += NTHR) z[q] = make_uint4(0, 0, 0, 0);
         if (threadIdx.x < NWARP) done[threadIdx.x] = 0;
+        const uint4* nt = reinterpret_cast<const uint4*>(lean_need_table<MT>());
+        for (int q = threadIdx.x; q < LeanNeed<MT, W>::BYTES / 16; q += NTHR) reinterpret_cast<uint4*>(need_s)[q] = nt[q];
     }
     __syncthreads();
     WinDev<T> winl = win;
@@ -196,11 +242,12 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
                 }
             }
             pos = hi;
-            // every other warp must have finished its colours < c before this window is read-modify-written
+            // the overlapping bins of earlier colours must be finished before this window is read-modify-written
             if (c > 0) {
+                const int need = (lane < NWARP) ? (int)need_s[(warp * NWARP + lane) * S3 + c] : 0;
                 for (;;) {
                     const int d = (lane < NWARP) ? lean_ld_acquire(done + lane) : S3;
-                    if (__all_sync(0xffffffffu, d >= c)) break;
+                    if (__all_sync(0xffffffffu, d >= need)) break;
                 }
             }
             // one read-modify-write of the window (cells beyond the padded tile carry zero weights only)
