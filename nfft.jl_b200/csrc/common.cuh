@@ -275,6 +275,7 @@ template <typename T> inline WinDev<T> make_win(const nfftb200_plan* p)
 // ---------------------------------------------------------------------------------------
 int nfftb_sort_nodes(nfftb200_plan* p, const void* d_k);                       // sort.cu
 int nfftb_ensure_bins(nfftb200_plan* p, int W, int G);
+int nfftb_ensure_bins_2d(nfftb200_plan* p);                                      // sort.cu: 2-D order by 8 x 8-cell bin inside a tile (xs2, perm2)
 int nfftb_ensure_cells_1d(nfftb200_plan* p);                                     // sort.cu: 1-D cell order (xs2, perm2, cell_start in d_bin_start)
 // lean.cu (kernel_mode 8, Float32 3-D): -1 when the kernels do not apply; scratch_override / slabs select the node-sharded forms
 int nfftb_spread_lean(nfftb200_plan* p, const void* fhat, void* g, void* scratch_override, int B, int t_lo, int t_hi);

@@ -66,6 +66,9 @@ void default_tiles(nfftb200_plan* p)
     const int D = p->D;
     for (int d = 0; d < D; d++) {
         int64_t v = (D == 1) ? 1024 : (D == 2 ? 64 : (d < 3 ? 16 : 1));      // _blockSize, src/precomputation.jl:59-77
+        // batched Float32 2-D plans: 16 x 16 tiles, so that the padded tiles of 32 transforms fit one CTA's shared memory
+        // (the batch-stationary kernels of twod_batch.cuh)
+        if (D == 2 && p->dtype == NFFTB200_F32 && p->B >= 8 && p->m <= 4) v = 16;
         p->bs[d] = std::min<int64_t>(v, p->Nt[d]);
     }
     if (D == 3) {

@@ -572,7 +572,107 @@ template <typename T> int cells1d_impl(nfftb200_plan* p)
     return NFFTB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 2-D: bin order for the batch-stationary spreader (twod_batch.cuh: k_spread_win2d).  Inside every tile the nodes are
+// grouped by bin = (8 cells along x) x (one row of cells) (key = lc1 * nq0 + lc0 / 8, ascending caller index inside a
+// bin): all nodes of a bin have their 2m <= 8 taps per dimension inside one register window of 16 columns x 8 rows.  Same two-pass
+// match_any ranking as k_bin_order; tile_start stays valid, the work items (n_lo, n_hi, stride) apply unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BINQ2D_MAX = 128;    // tiles of at most 32 x 32 cells: 4 column groups x 32 rows
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bin_order2d(const T* __restrict__ xs, const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_start, GeomDev g,
+              int nq0, int NQ, T* __restrict__ xs2, int32_t* __restrict__ perm2)
+{
+    __shared__ int wh[8][BINQ2D_MAX];
+    __shared__ int tot[BINQ2D_MAX + 1];
+    const int t = blockIdx.x;
+    const int lo = tile_start[t], hi = tile_start[t + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = t % g.nb[0], ty = t / g.nb[0];
+    const int c0 = tx * g.bs[0], c1 = ty * g.bs[1];
+    for (int q = threadIdx.x; q < 8 * BINQ2D_MAX; q += 256) (&wh[0][0])[q] = 0;
+    __syncthreads();
+    const int n = hi - lo;
+    const int per_warp = ((n + 8 * 32 - 1) / (8 * 32)) * 32;          // whole groups of 32 per warp
+    const int w_lo = lo + warp * per_warp, w_hi = min(hi, w_lo + per_warp);
+    const unsigned lt = (1u << lane) - 1u;
+    auto key_of = [&](int i) {
+        T ks;
+        const int l0 = node_cell<T>(xs[(long long)i * 2 + 0], g.Nt[0], ks) - c0;
+        const int l1 = node_cell<T>(xs[(long long)i * 2 + 1], g.Nt[1], ks) - c1;
+        return l1 * nq0 + (l0 >> 3);
+    };
+    for (int b0 = w_lo; b0 < w_hi; b0 += 32) {                         // pass 1: counts per (warp, bin)
+        const int i = b0 + lane;
+        const bool on = i < w_hi;
+        const int q = on ? key_of(i) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, q);
+        if (on && (peers & lt) == 0) wh[warp][q] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {                                            // exclusive offsets of the warps inside a bin
+        int run = 0;
+        for (int w = 0; w < 8; w++) { const int c = wh[w][threadIdx.x]; wh[w][threadIdx.x] = run; run += c; }
+        tot[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int q = 0; q < NQ; q++) { const int c = tot[q]; tot[q] = run; run += c; }
+    }
+    __syncthreads();
+    for (int b0 = w_lo; b0 < w_hi; b0 += 32) {                         // pass 2: place
+        const int i = b0 + lane;
+        const bool on = i < w_hi;
+        const int q = on ? key_of(i) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, q);
+        const int r = __popc(peers & lt);
+        int base = 0;
+        if (on) base = wh[warp][q];
+        __syncwarp();
+        if (on) {
+            const long long pos = (long long)lo + tot[q] + base + r;
+            xs2[pos * 2 + 0] = xs[(long long)i * 2 + 0];
+            xs2[pos * 2 + 1] = xs[(long long)i * 2 + 1];
+            perm2[pos] = perm[i];
+            if (r == 0) wh[warp][q] = base + __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T> int bins2d_impl(nfftb200_plan* p)
+{
+    if (p->D != 2 || p->bs[0] > 32 || p->bs[1] > 32) return nfftb_fail(p, NFFTB200_UNSUPPORTED, "2-D bin order: unsupported geometry");
+    const int nq0 = (int)(p->bs[0] + 7) / 8, NQ = nq0 * (int)p->bs[1];
+    if (p->have_bins && p->bins_nq == -100 - NQ) return NFFTB200_OK;
+    const int64_t M = std::max<int64_t>(p->M, 1);
+    if (M > p->cap_bins_nodes) {
+        if (p->d_xs2) cudaFree(p->d_xs2);
+        if (p->d_perm2) cudaFree(p->d_perm2);
+        p->d_xs2 = nullptr; p->d_perm2 = nullptr; p->cap_bins_nodes = 0;
+        CUDA_TRY(p, cudaMalloc(&p->d_xs2, (size_t)M * 3 * sizeof(T)));
+        CUDA_TRY(p, cudaMalloc((void**)&p->d_perm2, (size_t)M * 4));
+        p->cap_bins_nodes = M;
+    }
+    k_bin_order2d<T><<<(unsigned)p->ntiles, 256, 0, p->stream>>>((const T*)p->d_xs, p->d_perm, p->d_tile_start, make_geom<T>(p), nq0, NQ,
+                                                                (T*)p->d_xs2, p->d_perm2);
+    p->launches++;
+    CUDA_TRY(p, cudaGetLastError());
+    p->have_bins = true;
+    p->bins_nq = -100 - NQ;           // marks the 2-D bin order
+    return NFFTB200_OK;
+}
+
 }  // namespace
+
+int nfftb_ensure_bins_2d(nfftb200_plan* p)
+{
+    return p->dtype == NFFTB200_F32 ? bins2d_impl<float>(p) : bins2d_impl<double>(p);
+}
 
 int nfftb_ensure_cells_1d(nfftb200_plan* p)
 {

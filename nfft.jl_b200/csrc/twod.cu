@@ -7,6 +7,7 @@
 //    <= 4 tiles covering a grid cell and writes it once.  No atomics, deterministic, no memset.
 //  * interpolator: padded tile staged with cp.async, same lane mapping, 4 nodes reduced per shuffle butterfly.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tile3d.cuh"
@@ -42,6 +43,8 @@ template <typename T, int MT> struct Sub2 {
                sizeof(int) * T2_WARPS * 32 + sizeof(unsigned short) * T2_WARPS * 64 + T2_CHUNK;
     }
 };
+
+#include "twod_batch.cuh"
 
 template <typename T> __device__ __forceinline__ T wsum(T v)
 {
@@ -373,14 +376,133 @@ k_interp_row2d(const typename Cplx<T>::type* __restrict__ g, typename Cplx<T>::t
     }
 }
 
+// Float32 gather, two x-adjacent cells per thread (16-byte loads and stores).  Valid when m, the tile width and the grid
+// width are even: both cells then have the same covering tiles and every access is 16-byte aligned.  All item ranges of
+// the (up to four) covering tiles are fetched before the first scratch load is issued.
+template <int MT>
+__global__ void __launch_bounds__(128)
+k_gather_pairs2d(const float2* __restrict__ scratch, float2* __restrict__ g, const int32_t* __restrict__ tile_items, int tile_lo,
+                 int tile_hi, int item_lo, int item_hi, GeomDev geo)
+{
+    constexpr int L = 2 * MT;
+    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L;
+    const size_t PN = (size_t)PX * PY;
+    const int u0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int u1 = blockIdx.y, b = blockIdx.z;
+    if (u0 >= geo.Nt[0]) return;
+    scratch += (size_t)b * (item_hi - item_lo) * PN;
+    auto cover = [&](int u, int d, int (&tt)[2], int (&pc)[2]) -> int {
+        const int bs = geo.bs[d], nb = geo.nb[d], Nt = geo.Nt[d];
+        const int t = u / bs, l = u - t * bs;
+        const int len = (t == nb - 1) ? Nt - t * bs : bs;
+        int n = 0;
+        tt[n] = t; pc[n] = l + MT; n++;
+        if (l < MT) {
+            const int tp = t == 0 ? nb - 1 : t - 1;
+            const int lenp = (tp == nb - 1) ? Nt - tp * bs : bs;
+            tt[n] = tp; pc[n] = l + MT + lenp; n++;
+        } else if (l >= len - MT) {
+            tt[n] = t == nb - 1 ? 0 : t + 1; pc[n] = l + MT - len; n++;
+        }
+        return n;
+    };
+    int tx[2], px[2], ty[2], py[2];
+    const int nx = cover(u0, 0, tx, px), ny = cover(u1, 1, ty, py);
+    int i0[4], i1[4], off[4], np = 0;
+    for (int iy = 0; iy < ny; iy++)
+        for (int ix = 0; ix < nx; ix++) {
+            const int tile = ty[iy] * geo.nb[0] + tx[ix];
+            if (tile < tile_lo || tile >= tile_hi) continue;
+            i0[np] = tile_items[tile]; i1[np] = tile_items[tile + 1];
+            off[np] = py[iy] * PX + px[ix];
+            np++;
+        }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < np; q++)
+        for (int it = i0[q]; it < i1[q]; it++) {
+            const float4 c = *reinterpret_cast<const float4*>(scratch + (size_t)(it - item_lo) * PN + off[q]);
+            acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+        }
+    *reinterpret_cast<float4*>(g + (size_t)b * geo.gsz + (size_t)u1 * geo.Nt[0] + u0) = acc;
+}
+
+// batch-stationary kernels: transforms per warp (4, 2, 1 -> 32, 16, 8 transforms per CTA), or 0 if they do not apply
+template <int MT> int batch2d_tpw(const nfftb200_plan* p, const GeomDev& geo, int B)
+{
+    if (B < 8 || p->kernel_mode == 9 || p->kernel_mode == 1) return 0;
+    const Batch2<MT> lay(geo.bs);
+    for (int tpw = 4; tpw >= 1; tpw >>= 1) {
+        if (tpw > 1 && 8 * (tpw / 2) >= B) continue;                 // a smaller CTA batch already covers B
+        if (lay.bytes(8 * tpw) <= 227 * 1024) return tpw;
+    }
+    return 0;
+}
+
+template <int MT, int TPW>
+int spread_batch2d_go(nfftb200_plan* p, const void* fhat, int B, int item_lo, int item_hi, const GeomDev& geo)
+{
+    const Batch2<MT> lay(geo.bs);
+    const size_t smem = lay.bytes(8 * TPW);
+    auto kern = k_spread_batch2d<MT, TPW>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(item_hi - item_lo, (B + 8 * TPW - 1) / (8 * TPW));
+    kern<<<grid, TB_THREADS, smem, p->stream>>>((const float2*)fhat, (float2*)p->d_tilebuf, (const float*)p->d_xs, p->d_perm, p->d_items,
+                                                p->d_item_stride, item_lo, p->M, B, geo, make_win<float>(p), make_poly_param<float, MT>(p));
+    return NFFTB200_OK;
+}
+// register-window adjoint: tiles of 8..32 cells per dimension (so that a 16-cell window fits the padded tile)
+template <int MT> bool win2d_ok(const GeomDev& geo)
+{
+    const Batch2<MT> lay(geo.bs);
+    return geo.bs[0] + 2 * MT >= TW_WX && geo.bs[1] + 2 * MT >= TW_WY && geo.bs[0] <= 32 && geo.bs[1] <= 32 &&
+           Win2<MT>::bytes(lay) <= 227 * 1024;
+}
+template <int MT>
+int spread_win2d_go(nfftb200_plan* p, const void* fhat, int B, int item_lo, int item_hi, const GeomDev& geo)
+{
+    const Batch2<MT> lay(geo.bs);
+    const size_t smem = Win2<MT>::bytes(lay);
+    if (nfftb_ensure_bins_2d(p) != NFFTB200_OK) return -1;
+    auto kern = k_spread_win2d<MT>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    dim3 grid(item_hi - item_lo, (B + TW_BC - 1) / TW_BC);
+    kern<<<grid, TW_THREADS, smem, p->stream>>>((const float2*)fhat, (float2*)p->d_tilebuf, (const float*)p->d_xs2, p->d_perm2, p->d_items,
+                                                p->d_item_stride, item_lo, p->M, B, geo, make_win<float>(p), make_poly_param<float, MT>(p));
+    return NFFTB200_OK;
+}
+
+template <int MT, int TPW, int PXP>
+int interp_batch2d_pitch(nfftb200_plan* p, const void* g, void* fhat, int B, int item_lo, int item_hi, const GeomDev& geo)
+{
+    const Batch2<MT> lay(geo.bs);
+    const size_t smem = lay.bytes(8 * TPW);
+    auto kern = k_interp_batch2d<MT, TPW, PXP>;
+    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(item_hi - item_lo, (B + 8 * TPW - 1) / (8 * TPW));
+    kern<<<grid, TF_THREADS, smem, p->stream>>>((const float2*)g, (float2*)fhat, (const float*)p->d_xs, p->d_perm, p->d_items,
+                                                p->d_item_stride, item_lo, p->M, B, geo, make_win<float>(p), make_poly_param<float, MT>(p));
+    return NFFTB200_OK;
+}
+template <int MT, int TPW>
+int interp_batch2d_go(nfftb200_plan* p, const void* g, void* fhat, int B, int item_lo, int item_hi, const GeomDev& geo)
+{
+    const Batch2<MT> lay(geo.bs);
+    if (lay.PXp == 24) return interp_batch2d_pitch<MT, TPW, 24>(p, g, fhat, B, item_lo, item_hi, geo);
+    if (lay.PXp == 40) return interp_batch2d_pitch<MT, TPW, 40>(p, g, fhat, B, item_lo, item_hi, geo);
+    return interp_batch2d_pitch<MT, TPW, 0>(p, g, fhat, B, item_lo, item_hi, geo);
+}
+
 template <typename T, int MT>
 int spread2d_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo, int t_hi)
 {
     using C = typename Cplx<T>::type;
     GeomDev geo = make_geom<T>(p);
+    int tpw = 0;
+    if constexpr (std::is_same<T, float>::value && MT <= 4) tpw = batch2d_tpw<MT>(p, geo, B);
     Sub2<T, MT> lay(geo.bs);
     const size_t smem = lay.bytes();
-    if (smem > 227 * 1024 || lay.SX < 2 * MT || lay.SY < 2 * MT) return -1;
+    if (tpw == 0 && (smem > 227 * 1024 || lay.SX < 2 * MT || lay.SY < 2 * MT)) return -1;
     for (int d = 0; d < 2; d++) {
         const int last = geo.Nt[d] - (geo.nb[d] - 1) * geo.bs[d];
         if (geo.bs[d] < MT || last < MT) return -1;
@@ -394,16 +516,38 @@ int spread2d_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo
         if (cudaMalloc(&p->d_tilebuf, (size_t)need) != cudaSuccess) { cudaGetLastError(); return -1; }
         p->cap_tilebuf = need;
     }
-    auto kern = k_spread_sub2d<T, MT>;
-    CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(item_hi - item_lo, B);
-    if (item_hi > item_lo)
+    if constexpr (std::is_same<T, float>::value && MT <= 4) {
+        if (tpw && item_hi > item_lo) {
+            const int st = (win2d_ok<MT>(geo) && p->kernel_mode != 7) ? spread_win2d_go<MT>(p, fhat, B, item_lo, item_hi, geo)
+                         : tpw == 4 ? spread_batch2d_go<MT, 4>(p, fhat, B, item_lo, item_hi, geo)
+                         : tpw == 2 ? spread_batch2d_go<MT, 2>(p, fhat, B, item_lo, item_hi, geo)
+                                    : spread_batch2d_go<MT, 1>(p, fhat, B, item_lo, item_hi, geo);
+            if (st != NFFTB200_OK) return st;
+        }
+    }
+    if (tpw == 0 && item_hi > item_lo) {
+        auto kern = k_spread_sub2d<T, MT>;
+        CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(item_hi - item_lo, B);
         kern<<<grid, T2_THREADS, smem, p->stream>>>((const C*)fhat, (C*)p->d_tilebuf, (const T*)p->d_xs, p->d_perm,
                                                    p->d_items, p->d_item_stride, item_lo, p->M, geo, make_win<T>(p), make_poly_param<T, MT>(p));
-    int bx = 32;
-    while (bx < 256 && bx < geo.Nt[0]) bx <<= 1;
-    dim3 gg((geo.Nt[0] + bx - 1) / bx, geo.Nt[1], B);
-    k_gather_tiles2d<T, MT><<<gg, bx, 0, p->stream>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo);
+    }
+    bool pairs = false;
+    if constexpr (std::is_same<T, float>::value && MT % 2 == 0) {
+        // every tile at least 2m wide (so a cell has at most one neighbour tile per dimension), everything even
+        pairs = geo.bs[0] % 2 == 0 && geo.Nt[0] % 2 == 0 && geo.bs[0] >= 2 * MT && geo.bs[1] >= 2 * MT &&
+                geo.Nt[0] - (geo.nb[0] - 1) * geo.bs[0] >= 2 * MT && geo.Nt[1] - (geo.nb[1] - 1) * geo.bs[1] >= 2 * MT && p->kernel_mode != 9;
+        if (pairs) {
+            dim3 gg((geo.Nt[0] / 2 + 127) / 128, geo.Nt[1], B);
+            k_gather_pairs2d<MT><<<gg, 128, 0, p->stream>>>((const float2*)p->d_tilebuf, (float2*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo);
+        }
+    }
+    if (!pairs) {
+        int bx = 32;
+        while (bx < 256 && bx < geo.Nt[0]) bx <<= 1;
+        dim3 gg((geo.Nt[0] + bx - 1) / bx, geo.Nt[1], B);
+        k_gather_tiles2d<T, MT><<<gg, bx, 0, p->stream>>>((const C*)p->d_tilebuf, (C*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo);
+    }
     p->launches += 2;
     CUDA_TRY(p, cudaGetLastError());
     return NFFTB200_OK;
@@ -414,12 +558,25 @@ int interp2d_launch(nfftb200_plan* p, const void* g, void* fhat, int B, int t_lo
 {
     using C = typename Cplx<T>::type;
     GeomDev geo = make_geom<T>(p);
+    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
+    if constexpr (std::is_same<T, float>::value && MT <= 4) {
+        const int tpw = batch2d_tpw<MT>(p, geo, B);
+        if (tpw) {
+            if (item_hi == item_lo) return NFFTB200_OK;
+            const int st = tpw == 4 ? interp_batch2d_go<MT, 4>(p, g, fhat, B, item_lo, item_hi, geo)
+                         : tpw == 2 ? interp_batch2d_go<MT, 2>(p, g, fhat, B, item_lo, item_hi, geo)
+                                    : interp_batch2d_go<MT, 1>(p, g, fhat, B, item_lo, item_hi, geo);
+            if (st != NFFTB200_OK) return st;
+            p->launches++;
+            CUDA_TRY(p, cudaGetLastError());
+            return NFFTB200_OK;
+        }
+    }
     Interp2<T, MT> lay(geo.bs);
     const size_t smem = lay.bytes();
     if (smem > 227 * 1024) return -1;
     auto kern = k_interp_row2d<T, MT>;
     CUDA_TRY(p, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int item_lo = p->h_tile_items[(size_t)t_lo], item_hi = p->h_tile_items[(size_t)t_hi];
     if (item_hi == item_lo) return NFFTB200_OK;
     dim3 grid(item_hi - item_lo, B);
     kern<<<grid, T2_THREADS, smem, p->stream>>>((const C*)g, (C*)fhat, (const T*)p->d_xs, p->d_perm, p->d_items, p->d_item_stride,
