@@ -247,16 +247,27 @@ k_spread_win2d(const float2* __restrict__ fhat, float2* __restrict__ scratch, co
             reinterpret_cast<int*>(dst)[WW + WY + 1] = org;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TW_PROD * 32) : "memory");          // caller indices of the whole chunk are in place
+        // coefficient gather: all caller indices, then all global loads, then all stores -- written out so that no load
+        // waits behind a shared-memory store it might alias (the first version ran its 16 round trips one after another)
         C* vb = val + buf * BC * NCH;
         const int* pb = pidx + buf * NCH;
+        constexpr int U = BC * NCH / (TW_PROD * 32);
+        int pn[U];
 #pragma unroll
-        for (int u = 0; u < BC * NCH / (TW_PROD * 32); u++) {
+        for (int u = 0; u < U; u++) {
             const int idx = u * (TW_PROD * 32) + pw * 32 + lane;
             const int n = idx & (NCH - 1), t = idx / NCH;
-            C v = make_float2(0.f, 0.f);
-            if (n < nc && t < nbt) v = fhat[(long long)(b0 + t) * M + pb[n]];
-            vb[idx] = v;
+            pn[u] = (n < nc && t < nbt) ? pb[n] : -1;
         }
+        C vv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int t = (u * (TW_PROD * 32) + pw * 32 + lane) / NCH;
+            vv[u] = make_float2(0.f, 0.f);
+            if (pn[u] >= 0) vv[u] = fhat[(long long)(b0 + t) * M + pn[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) vb[u * (TW_PROD * 32) + pw * 32 + lane] = vv[u];
     };
 
     {
@@ -412,13 +423,18 @@ k_interp_batch2d(const float2* __restrict__ g, float2* __restrict__ fhat, const 
     } else {                                                                     // toBlock!: the padded tiles of my transforms
         const int x0 = cx0 - MT, y0 = cy0 - MT;
         const bool fw = PX <= geo.Nt[0] && PY <= geo.Nt[1];
-        for (int r = warp; r < nbt * PY; r += 8) {
-            const int t = r / PY, y = r - t * PY;
-            const C* src = g + (long long)(b0 + t) * geo.gsz + (size_t)wrapc(y0 + y, geo.Nt[1], fw) * geo.Nt[0];
-            C* dst = planes + (size_t)t * PP + y * PXp;
-            for (int x = lane; x < PXp; x += 32) {
-                if (x < PX) cp_async_cell(dst + x, src + wrapc(x0 + x, geo.Nt[0], fw));
-                else dst[x] = make_float2(0.f, 0.f);                            // pitch padding: read with zero weights
+        const C* gb = g + (long long)b0 * geo.gsz;
+        for (int xb = 0; xb < PXp; xb += 32) {                                   // one pass for tiles of up to 24 cells
+            const int x = xb + lane;
+            const int xg = x < PX ? wrapc(x0 + x, geo.Nt[0], fw) : -1;           // -1: pitch padding, read with zero weights
+            for (int y = warp; y < PY; y += 8) {
+                const C* src = gb + (size_t)wrapc(y0 + y, geo.Nt[1], fw) * geo.Nt[0] + xg;
+                C* dst = planes + y * PXp + x;
+                if (xg >= 0) {
+                    for (int t = 0; t < nbt; t++, src += geo.gsz, dst += PP) cp_async_cell(dst, src);
+                } else if (x < PXp) {
+                    for (int t = 0; t < nbt; t++, dst += PP) *dst = make_float2(0.f, 0.f);
+                }
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
