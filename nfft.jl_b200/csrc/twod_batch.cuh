@@ -182,7 +182,7 @@ template <int MT> struct Win2 {
     static size_t bytes(const Batch2<MT>& lay)
     {
         return sizeof(float2) * (size_t)lay.PP * TW_BC + 2 * sizeof(float2) * (size_t)TB_NCH * TW_BC +
-               2 * (sizeof(float) * TB_NCH * TW_REC + sizeof(int) * TB_NCH);
+               3 * (sizeof(float) * TB_NCH * TW_REC + sizeof(int) * TB_NCH);
     }
 };
 
@@ -200,8 +200,8 @@ k_spread_win2d(const float2* __restrict__ fhat, float2* __restrict__ scratch, co
     const int PX = lay.PX, PY = lay.PY, PXp = lay.PXp, PP = lay.PP;
     C* planes = reinterpret_cast<C*>(smem_raw);                                  // [BC][PP]
     C* val = planes + (size_t)PP * BC;                                           // [2][BC][NCH]
-    float* rec = reinterpret_cast<float*>(val + 2 * BC * NCH);                   // [2][NCH][REC]: wx16 | wy8 | bin | window origin | pad
-    int* pidx = reinterpret_cast<int*>(rec + 2 * NCH * REC);                     // [2][NCH]
+    float* rec = reinterpret_cast<float*>(val + 2 * BC * NCH);                   // [3][NCH][REC]: wx16 | wy8 | bin | window origin | pad
+    int* pidx = reinterpret_cast<int*>(rec + 3 * NCH * REC);                     // [3][NCH]
 
     const int32_t* item = items + 3 * (size_t)(item_lo + blockIdx.x);
     const int tile_id = item[0];
@@ -216,11 +216,14 @@ k_spread_win2d(const float2* __restrict__ fhat, float2* __restrict__ scratch, co
     const int nch = (n_item + NCH - 1) / NCH;
     const int nq0 = (geo.bs[0] + 7) >> 3;
 
-    auto stage = [&](int k) {                                                     // the two producer warps: chunk k -> buffer k & 1
-        const int buf = k & 1, cbase = k * NCH, nc = min(NCH, n_item - cbase);
-        const int pw = warp - TW_CONS;
-        {
-            const int n = pw * 32 + lane;
+    // Producer pipeline, one global round trip per warp and pass: warp 8 evaluates the taps (and caller indices) of chunk
+    // k + 2 into record buffer (k + 2) % 3 while warp 9 gathers the coefficients of chunk k + 1 -- whose caller indices
+    // were staged one pass earlier -- into value buffer (k + 1) & 1, and the consumers work on chunk k.
+    auto stage_taps = [&](int k) {
+        const int buf = k % 3, cbase = k * NCH, nc = min(NCH, n_item - cbase);
+#pragma unroll
+        for (int h = 0; h < NCH / 32; h++) {
+            const int n = h * 32 + lane;
             float* dst = rec + (buf * NCH + n) * REC;
 #pragma unroll
             for (int q = 0; q < (WW + WY) / 4; q++) reinterpret_cast<float4*>(dst)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -246,28 +249,33 @@ k_spread_win2d(const float2* __restrict__ fhat, float2* __restrict__ scratch, co
             reinterpret_cast<int*>(dst)[WW + WY] = qbin;
             reinterpret_cast<int*>(dst)[WW + WY + 1] = org;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(TW_PROD * 32) : "memory");          // caller indices of the whole chunk are in place
-        // coefficient gather: all caller indices, then all global loads, then all stores -- written out so that no load
-        // waits behind a shared-memory store it might alias (the first version ran its 16 round trips one after another)
-        C* vb = val + buf * BC * NCH;
-        const int* pb = pidx + buf * NCH;
-        constexpr int U = BC * NCH / (TW_PROD * 32);
-        int pn[U];
+    };
+    // coefficient gather: all caller indices, then all global loads, then all stores -- written out so that no load
+    // waits behind a shared-memory store it might alias (the first version ran its round trips one after another)
+    auto stage_vals = [&](int k) {
+        const int nc = min(NCH, n_item - k * NCH);
+        C* vb = val + (k & 1) * BC * NCH;
+        const int* pb = pidx + (k % 3) * NCH;
+        constexpr int U = 16;
+#pragma unroll 1
+        for (int u0 = 0; u0 < BC * NCH / 32; u0 += U) {
+            int pn[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int idx = u * (TW_PROD * 32) + pw * 32 + lane;
-            const int n = idx & (NCH - 1), t = idx / NCH;
-            pn[u] = (n < nc && t < nbt) ? pb[n] : -1;
+            for (int u = 0; u < U; u++) {
+                const int idx = (u0 + u) * 32 + lane;
+                const int n = idx & (NCH - 1), t = idx / NCH;
+                pn[u] = (n < nc && t < nbt) ? pb[n] : -1;
+            }
+            C vv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int t = ((u0 + u) * 32 + lane) / NCH;
+                vv[u] = make_float2(0.f, 0.f);
+                if (pn[u] >= 0) vv[u] = fhat[(long long)(b0 + t) * M + pn[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) vb[(u0 + u) * 32 + lane] = vv[u];
         }
-        C vv[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int t = (u * (TW_PROD * 32) + pw * 32 + lane) / NCH;
-            vv[u] = make_float2(0.f, 0.f);
-            if (pn[u] >= 0) vv[u] = fhat[(long long)(b0 + t) * M + pn[u]];
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) vb[u * (TW_PROD * 32) + pw * 32 + lane] = vv[u];
     };
 
     {
@@ -275,20 +283,19 @@ k_spread_win2d(const float2* __restrict__ fhat, float2* __restrict__ scratch, co
         const int n16 = (int)((sizeof(C) * (size_t)PP * BC) / 16);
         for (int q = threadIdx.x; q < n16; q += TW_THREADS) z[q] = make_uint4(0, 0, 0, 0);
     }
-    if (warp >= TW_CONS) stage(0);
-    __syncthreads();
-
     const int i = lane & 15, tl = 2 * warp + (lane >> 4);                        // my window column, my transform (CTA-local)
     C* plane = planes + (size_t)(warp < TW_CONS ? tl : 0) * PP + i;
     C c[WY];
     int cur = -1, curoff = 0;
-    for (int k = 0; k < nch; k++) {
-        if (warp >= TW_CONS) {
-            if (k + 1 < nch) stage(k + 1);
-        } else {
-            const int buf = k & 1, nc = min(NCH, n_item - k * NCH);
-            const float* rw = rec + buf * NCH * REC;
-            const C* vb = val + (buf * BC + tl) * NCH;
+    for (int k = -2; k < nch; k++) {
+        if (warp == TW_CONS) {
+            if (k + 2 < nch) stage_taps(k + 2);
+        } else if (warp == TW_CONS + 1) {
+            if (k + 1 >= 0 && k + 1 < nch) stage_vals(k + 1);
+        } else if (k >= 0) {
+            const int nc = min(NCH, n_item - k * NCH);
+            const float* rw = rec + (k % 3) * NCH * REC;
+            const C* vb = val + ((k & 1) * BC + tl) * NCH;
             auto load_node = [&](const float* r, const C* vp, float& wxi, C& v, float4 (&wy)[WY / 4], int& q, int& org) {
                 wxi = r[i];
                 v = *vp;
