@@ -426,6 +426,91 @@ k_gather_pairs2d(const float2* __restrict__ scratch, float2* __restrict__ g, con
     *reinterpret_cast<float4*>(g + (size_t)b * geo.gsz + (size_t)u1 * geo.Nt[0] + u0) = acc;
 }
 
+// Float32 gather for batched plans, one CTA per output tile and group of transforms: the covering pieces of a pair of
+// cells (offsets into the padded tiles of the tile itself and of its neighbours) are worked out once and reused for
+// every transform of the group, whose loads are independent of each other (four transforms in flight per thread when
+// every covering tile has a single work item, the common case).  Same validity conditions as k_gather_pairs2d.
+template <int MT>
+__global__ void __launch_bounds__(128)
+k_gather_tile2d(const float2* __restrict__ scratch, float2* __restrict__ g, const int32_t* __restrict__ tile_items, int tile_lo,
+                int tile_hi, int item_lo, int item_hi, int B, int bper, GeomDev geo)
+{
+    constexpr int L = 2 * MT;
+    const int PX = geo.bs[0] + L, PY = geo.bs[1] + L;
+    const size_t PN = (size_t)PX * PY, SB = (size_t)(item_hi - item_lo) * PN;
+    const int tile = blockIdx.x, tx = tile % geo.nb[0], ty = tile / geo.nb[0];
+    const int b_lo = blockIdx.y * bper, b_hi = min(B, b_lo + bper);
+    auto tlen = [&](int t, int d) { return t == geo.nb[d] - 1 ? geo.Nt[d] - t * geo.bs[d] : geo.bs[d]; };
+    const int len0 = tlen(tx, 0), len1 = tlen(ty, 1), hp = len0 >> 1;
+    auto cover = [&](int t, int l, int len, int d, int (&tt)[2], int (&pc)[2]) -> int {
+        const int nb = geo.nb[d];
+        int n = 0;
+        tt[n] = t; pc[n] = l + MT; n++;
+        if (l < MT) {
+            const int tp = t == 0 ? nb - 1 : t - 1;
+            tt[n] = tp; pc[n] = l + MT + tlen(tp, d); n++;
+        } else if (l >= len - MT) {
+            tt[n] = t == nb - 1 ? 0 : t + 1; pc[n] = l + MT - len; n++;
+        }
+        return n;
+    };
+    for (int idx = threadIdx.x; idx < hp * len1; idx += blockDim.x) {
+        const int l1 = idx / hp, l0 = 2 * (idx - l1 * hp);
+        int txs[2], pxs[2], tys[2], pys[2];
+        const int nx = cover(tx, l0, len0, 0, txs, pxs), ny = cover(ty, l1, len1, 1, tys, pys);
+        int i0[4], i1[4], np = 0;
+        size_t off[4];
+        bool single = true;
+        for (int iy = 0; iy < ny; iy++)
+            for (int ix = 0; ix < nx; ix++) {
+                const int t = tys[iy] * geo.nb[0] + txs[ix];
+                if (t < tile_lo || t >= tile_hi) continue;
+                i0[np] = tile_items[t]; i1[np] = tile_items[t + 1];
+                if (i1[np] == i0[np]) continue;                                  // empty tile: no scratch block
+                single = single && i1[np] == i0[np] + 1;
+                off[np] = (size_t)(i0[np] - item_lo) * PN + (size_t)pys[iy] * PX + pxs[ix];
+                np++;
+            }
+        float2* out = g + (size_t)(ty * geo.bs[1] + l1) * geo.Nt[0] + tx * geo.bs[0] + l0;
+        if (single) {
+            int b = b_lo;
+            for (; b + 4 <= b_hi; b += 4) {
+                float4 c[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        c[u][q] = q < np ? *reinterpret_cast<const float4*>(scratch + (size_t)(b + u) * SB + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float4 a = c[u][0];
+#pragma unroll
+                    for (int q = 1; q < 4; q++) { a.x += c[u][q].x; a.y += c[u][q].y; a.z += c[u][q].z; a.w += c[u][q].w; }
+                    *reinterpret_cast<float4*>(out + (size_t)(b + u) * geo.gsz) = a;
+                }
+            }
+            for (; b < b_hi; b++) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < np; q++) {
+                    const float4 c = *reinterpret_cast<const float4*>(scratch + (size_t)b * SB + off[q]);
+                    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+                }
+                *reinterpret_cast<float4*>(out + (size_t)b * geo.gsz) = a;
+            }
+        } else {
+            for (int b = b_lo; b < b_hi; b++) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < np; q++)
+                    for (int it = 0; it < i1[q] - i0[q]; it++) {
+                        const float4 c = *reinterpret_cast<const float4*>(scratch + (size_t)b * SB + off[q] + (size_t)it * PN);
+                        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+                    }
+                *reinterpret_cast<float4*>(out + (size_t)b * geo.gsz) = a;
+            }
+        }
+    }
+}
+
 // batch-stationary kernels: transforms per warp (4, 2, 1 -> 32, 16, 8 transforms per CTA), or 0 if they do not apply
 template <int MT> int batch2d_tpw(const nfftb200_plan* p, const GeomDev& geo, int B)
 {
@@ -537,7 +622,12 @@ int spread2d_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo
         // every tile at least 2m wide (so a cell has at most one neighbour tile per dimension), everything even
         pairs = geo.bs[0] % 2 == 0 && geo.Nt[0] % 2 == 0 && geo.bs[0] >= 2 * MT && geo.bs[1] >= 2 * MT &&
                 geo.Nt[0] - (geo.nb[0] - 1) * geo.bs[0] >= 2 * MT && geo.Nt[1] - (geo.nb[1] - 1) * geo.bs[1] >= 2 * MT && p->kernel_mode != 9;
-        if (pairs) {
+        if (pairs && B >= 8 && p->ntiles <= 0x7fffffff / 8 && p->kernel_mode != 7) {
+            const int bper = 8;
+            dim3 gg((unsigned)p->ntiles, (B + bper - 1) / bper);
+            k_gather_tile2d<MT><<<gg, 128, 0, p->stream>>>((const float2*)p->d_tilebuf, (float2*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi,
+                                                           B, bper, geo);
+        } else if (pairs) {
             dim3 gg((geo.Nt[0] / 2 + 127) / 128, geo.Nt[1], B);
             k_gather_pairs2d<MT><<<gg, 128, 0, p->stream>>>((const float2*)p->d_tilebuf, (float2*)g, p->d_tile_items, t_lo, t_hi, item_lo, item_hi, geo);
         }

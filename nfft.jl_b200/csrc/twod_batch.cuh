@@ -356,8 +356,8 @@ k_spread_win2d(const float2* __restrict__ fhat, float2* __restrict__ scratch, co
 // ------------------------------------------------------------------------------------------------------
 // Forward.  First B200 measurement of the straightforward form (one node at a time, 3-stage shuffle sum per node):
 // 2.14 ms on C3, 88 issue slots per (node, warp), stalls on fixed-latency dependencies with two warps per scheduler.
-// This form works on 4 nodes at a time -- four independent load / FMA chains -- and folds their 4 x (re, im) partial
-// sums over the 8 column lanes with one halving butterfly (7 shuffles instead of 24); the tap rows are read with
+// This form works on 8 nodes at a time -- eight independent load / FMA chains -- and folds their partial sums over
+// the 8 column lanes with one halving butterfly (14 shuffles instead of 48); the tap rows are read with
 // 16-byte loads and the row pitch is a compile-time constant for 16- and 32-cell tiles (PXP; 0 = run time).
 constexpr int TF_PROD = 2, TF_THREADS = (8 + TF_PROD) * 32, TF_REC = 16;
 
@@ -462,11 +462,11 @@ k_interp_batch2d(const float2* __restrict__ g, float2* __restrict__ fhat, const 
             const int buf = k & 1, nc = min(NCH, n_item - k * NCH);
             const float* rb = rec + buf * NCH * REC;
             const int* bb = base + buf * NCH;
-            float* ob = reinterpret_cast<float*>(res + (buf * BC + tl) * NCH);
-            for (int n0 = 0; n0 < nc; n0 += 4, rb += 4 * REC, bb += 4) {
-                C acc[4];
+            C* ob = res + (buf * BC + tl) * NCH;
+            for (int n0 = 0; n0 < nc; n0 += 8, rb += 8 * REC, bb += 8) {
+                C acc[8];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < 8; q++) {
                     const float* rw = rb + q * REC;
                     const C* p = plane + bb[q];
                     const float4 wa = reinterpret_cast<const float4*>(rw + 8)[0], wb = reinterpret_cast<const float4*>(rw + 8)[1];
@@ -483,22 +483,23 @@ k_interp_batch2d(const float2* __restrict__ g, float2* __restrict__ fhat, const 
                     }
                     acc[q] = a;
                 }
-                // halving butterfly over the 8 column lanes: lane i ends with component (i & 1) of node n0 + (i >> 1)
-                C h0, h1;
-                {
-                    const C k0 = up4 ? acc[2] : acc[0], k1 = up4 ? acc[3] : acc[1];
-                    const C s0 = up4 ? acc[0] : acc[2], s1 = up4 ? acc[1] : acc[3];
-                    h0.x = k0.x + __shfl_xor_sync(0xffffffffu, s0.x, 4); h0.y = k0.y + __shfl_xor_sync(0xffffffffu, s0.y, 4);
-                    h1.x = k1.x + __shfl_xor_sync(0xffffffffu, s1.x, 4); h1.y = k1.y + __shfl_xor_sync(0xffffffffu, s1.y, 4);
+                // halving butterfly over the 8 column lanes: lane i ends with the sum of node n0 + i
+                C h[4], e[2], f;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const C kk = up4 ? acc[4 + j] : acc[j], ss = up4 ? acc[j] : acc[4 + j];
+                    h[j].x = kk.x + __shfl_xor_sync(0xffffffffu, ss.x, 4); h[j].y = kk.y + __shfl_xor_sync(0xffffffffu, ss.y, 4);
                 }
-                C e;
-                {
-                    const C kk = up2 ? h1 : h0, ss = up2 ? h0 : h1;
-                    e.x = kk.x + __shfl_xor_sync(0xffffffffu, ss.x, 2); e.y = kk.y + __shfl_xor_sync(0xffffffffu, ss.y, 2);
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const C kk = up2 ? h[2 + j] : h[j], ss = up2 ? h[j] : h[2 + j];
+                    e[j].x = kk.x + __shfl_xor_sync(0xffffffffu, ss.x, 2); e[j].y = kk.y + __shfl_xor_sync(0xffffffffu, ss.y, 2);
                 }
-                const float kf = up1 ? e.y : e.x, sf = up1 ? e.x : e.y;
-                const float tot = kf + __shfl_xor_sync(0xffffffffu, sf, 1);
-                if (r0 == 0 && n0 + (i >> 1) < nc) ob[2 * n0 + i] = tot;
+                {
+                    const C kk = up1 ? e[1] : e[0], ss = up1 ? e[0] : e[1];
+                    f.x = kk.x + __shfl_xor_sync(0xffffffffu, ss.x, 1); f.y = kk.y + __shfl_xor_sync(0xffffffffu, ss.y, 1);
+                }
+                if (r0 == 0 && n0 + i < nc) ob[n0 + i] = f;
             }
         }
         __syncthreads();
