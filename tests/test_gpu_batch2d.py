@@ -42,8 +42,9 @@ def check(nb, k, N, m, B, **kw):
     fwd9 = np.asarray(p * f)
     adj9 = np.asarray(p.adjoint() * fh)
     assert rel(fwd, fwd9) <= 2e-6 and rel(adj, adj9) <= 2e-6
-    p.set_kernel_mode(7)                                   # read-modify-write form of the batched adjoint
+    p.set_kernel_mode(7)                                   # the batch-stationary kernels without register windows
     assert rel(np.asarray(p.adjoint() * fh), adj9) <= 2e-6
+    assert rel(np.asarray(p * f), fwd9) <= 2e-6
     for b in sorted({0, 1, B // 2, B - 1}):
         ef = rel(fwd[:, b], po.forward(np.asfortranarray(f[..., b])))
         ea = rel(adj[..., b], po.adjoint(np.ascontiguousarray(fh[:, b])))
