@@ -513,3 +513,6 @@ k_interp_batch2d(const float2* __restrict__ g, float2* __restrict__ fhat, const 
 // lanes shared by 4 nodes) was built and measured on C3: 1.25 ms against 1.06 ms for k_interp_batch2d.  It takes the
 // shared-memory traffic away but needs 20 issue slots per (node, transform) instead of 10 -- the column reduction over
 // 16 lanes and the half-empty 16-tap column weights -- so the direct form stays.
+// A row-window forward kernel (lane (tap row, transform) holds 16 columns of the bin's window: exact rows, 3-stage
+// reduction shared by 8 nodes, records only in shared memory) was measured as well: 1.05 ms, 53 issue slots per
+// (node, warp) at 1.5 IPC -- no better than the direct form, which needs neither the bin order nor a second layout.
