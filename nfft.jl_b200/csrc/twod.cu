@@ -584,10 +584,16 @@ int spread2d_launch(nfftb200_plan* p, const void* fhat, void* g, int B, int t_lo
     using C = typename Cplx<T>::type;
     GeomDev geo = make_geom<T>(p);
     int tpw = 0;
-    if constexpr (std::is_same<T, float>::value && MT <= 4) tpw = batch2d_tpw<MT>(p, geo, B);
     Sub2<T, MT> lay(geo.bs);
     const size_t smem = lay.bytes();
-    if (tpw == 0 && (smem > 227 * 1024 || lay.SX < 2 * MT || lay.SY < 2 * MT)) return -1;
+    const bool sub_ok = smem <= 227 * 1024 && lay.SX >= 2 * MT && lay.SY >= 2 * MT;
+    if constexpr (std::is_same<T, float>::value && MT <= 4) {
+        tpw = batch2d_tpw<MT>(p, geo, B);
+        // without the register windows (tile too large / too small for them) the per-transform kernel is the faster
+        // adjoint: the read-modify-write form is kept for tiles it cannot take, and as kernel_mode 7
+        if (tpw && !win2d_ok<MT>(geo) && sub_ok && p->kernel_mode != 7) tpw = 0;
+    }
+    if (tpw == 0 && !sub_ok) return -1;
     for (int d = 0; d < 2; d++) {
         const int last = geo.Nt[d] - (geo.nb[d] - 1) * geo.bs[d];
         if (geo.bs[d] < MT || last < MT) return -1;
