@@ -148,7 +148,9 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
  *       staged by a TMA tensor map, LINEAR table staged by a bulk TMA copy); other 3-D plans the warp-private sub-tile
  *       spreader (per-tile sub-grids stored with TMA bulk copies) and the row-per-lane interpolator; a gather pass sums
  *       the per-tile sub-grids; 1-D plans work on a plan-time cell order; 3-D FFT pruned to the z-planes that carry
- *       image frequencies; D = 4 runs on the generic kernels,
+ *       image frequencies; D = 4 runs on the generic kernels.  Float32 2-D plans with ntransforms >= 8 (default tile
+ *       16 x 16) run the batch-stationary kernels of csrc/twod_batch.cuh: one CTA keeps the padded tile of 16 / 32
+ *       transforms in shared memory, producer warps evaluate the window taps once per node for the whole batch,
  *   1 = force the generic warp-per-node kernels (global vector REDs),
  *   2 = tiled spreader with the halo flushed by vector REDs instead of scratch + gather,
  *   3 = auto, but the interpolator never uses the TMA tensor-map load,
@@ -161,9 +163,11 @@ int nfftb200_get_kernel_times(nfftb200_plan* p, double out[4]);
  *       of a bin are summed in registers; falls back to mode 0 where they do not apply (node-sharded plans use the
  *       spreader for the peer scratch and the slab-direct form of the interpolator).  Experimental: verified by
  *       host emulation of the kernel sources (tests/emu); measured on B200 in round 2 (661 / 491 us on C2).
+ *       Batched Float32 2-D plans: the batch-stationary kernels without the register windows of the adjoint.
  *   8 = force the (tile, bin)-ordered register-window kernels (csrc/spread_lean.cuh, csrc/interp_lean.cuh): Float32,
  *       3-D, m = 2 or 3, tiles of at most 16 cells.  Mode 0 already selects them where they apply.
- *   9 = the round-1 default: warp-private sub-tile spreader / row-per-lane interpolator for every 3-D plan.
+ *   9 = the round-1 default: warp-private sub-tile spreader / row-per-lane interpolator for every 3-D plan; the
+ *       per-transform kernels for batched 2-D plans.
  *  13 = mode 8 with thread-block clusters of two x-adjacent tiles that merge their shared halo through distributed
  *       shared memory and write one 38-column block to the scratch (experiment).
  *  12 = mode 8 with the compact tile layout in the interpolator (no TMA box load, 8-byte window loads).
