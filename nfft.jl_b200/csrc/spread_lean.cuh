@@ -189,7 +189,7 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
             for (int p = 0; p < NP; p++) acc[p].zero();
             int o0 = 0, o1 = 0, o2 = 0;                                      // window origin of the bin, padded-tile coordinates
             const int lo = pos;
-            for (int i = lo; i < hi; i++) {
+            for (int i = lo; i < hi;) {
                 if (i >= rbase + RND) {                                      // warp-uniform: next round of records
                     __syncwarp();                                            // the previous round has been read
                     rbase = i;
@@ -232,13 +232,18 @@ k_spread_lean(const float2* __restrict__ fhat, float2* __restrict__ scratch, con
                     const int4 org = *reinterpret_cast<const int4*>(rn + 4 * W);
                     o0 = org.x; o1 = org.y; o2 = org.z;
                 }
-                T wx[W];
-                bin_load_row<T, W>(rn, wx);
-                const T wy = rn[W + rowy];
+                // the bin's nodes inside the resident round: a tight run with one pointer increment per node
+                const T* rend = myrec + (min(hi, rbase + RND) - rbase) * RW;
+                i = min(hi, rbase + RND);
+                for (; rn < rend; rn += RW) {
+                    T wx[W];
+                    bin_load_row<T, W>(rn, wx);
+                    const T wy = rn[W + rowy];
 #pragma unroll
-                for (int p = 0; p < NP; p++) {
-                    const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz + 4 * p];
-                    acc[p].axpy(wx, wy, vz);
+                    for (int p = 0; p < NP; p++) {
+                        const C vz = reinterpret_cast<const C*>(rn + 2 * W)[rowz + 4 * p];
+                        acc[p].axpy(wx, wy, vz);
+                    }
                 }
             }
             pos = hi;
