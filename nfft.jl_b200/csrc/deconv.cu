@@ -28,11 +28,9 @@ __device__ __forceinline__ int grid_index(int i, int N, int Nt)
 
 // One thread writes one 16-byte unit of the grid (two Float32 cells or one Float64 cell); row
 // quantities (u1,u2 -> i1,i2, LUT factors) are block-uniform.  blockIdx.z = u2 + Nt2 * batch.
-// One thread writes 16 bytes of DECONV_ROWS consecutive grid rows (65 536 blocks of 128 threads were block-scheduling
-// bound on C2: 50 us for 134 MB of plain stores).
-constexpr int DECONV_ROWS = 8;
-
-template <typename T>
+// One thread writes 16 bytes of DECONV_ROWS (8, or 1 for small / 1-D grids) consecutive grid rows: 65 536 blocks of 128
+// threads were block-scheduling bound on C2 (50 us for 134 MB of plain stores).
+template <typename T, int DECONV_ROWS>
 __global__ void __launch_bounds__(256)
 k_deconv_fwd(const typename Cplx<T>::type* __restrict__ f, typename Cplx<T>::type* __restrict__ g,
              GeomDev geo, const T* __restrict__ lut)
@@ -196,8 +194,14 @@ template <typename T> int deconv_impl(nfftb200_plan* p, const void* src, void* d
         const int units = (geo.Nt[0] + VPC - 1) / VPC;                      // Nt[0] is even
         int bx = 32;
         while (bx < 256 && bx < units) bx <<= 1;
-        grid = dim3((units + bx - 1) / bx, (geo.Nt[1] + DECONV_ROWS - 1) / DECONV_ROWS, geo.Nt[2] * geo.Nt[3] * B);
-        k_deconv_fwd<T><<<grid, bx, 0, p->stream>>>((const C*)src, (C*)dst, geo, (const T*)p->d_hat_inv);
+        const long long blocks8 = (long long)((units + bx - 1) / bx) * ((geo.Nt[1] + 7) / 8) * geo.Nt[2] * geo.Nt[3] * B;
+        if (geo.Nt[1] >= 8 && blocks8 >= 8 * 148) {
+            grid = dim3((units + bx - 1) / bx, (geo.Nt[1] + 7) / 8, geo.Nt[2] * geo.Nt[3] * B);
+            k_deconv_fwd<T, 8><<<grid, bx, 0, p->stream>>>((const C*)src, (C*)dst, geo, (const T*)p->d_hat_inv);
+        } else {
+            grid = dim3((units + bx - 1) / bx, geo.Nt[1], geo.Nt[2] * geo.Nt[3] * B);
+            k_deconv_fwd<T, 1><<<grid, bx, 0, p->stream>>>((const C*)src, (C*)dst, geo, (const T*)p->d_hat_inv);
+        }
     } else {
         launch_dims(geo.N[0], geo.N[1], geo.N[2] * geo.N[3], grid, block);
         k_deconv_adj<T><<<grid, block, 0, p->stream>>>((const C*)src, (C*)dst, geo,
