@@ -310,6 +310,7 @@ k_spread_win2d(const float2* __restrict__ fhat, float2* __restrict__ scratch, co
 #pragma unroll
                         for (int y = 0; y < WY; y++) plane[curoff + y * PXp] = c[y];
                     }
+                    __syncwarp();                                                // overlapping windows: another lane's column
                     cur = q; curoff = org;
 #pragma unroll
                     for (int y = 0; y < WY; y++) c[y] = plane[curoff + y * PXp];
