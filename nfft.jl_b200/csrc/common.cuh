@@ -140,6 +140,9 @@ struct nfftb200_plan {
     int32_t* d_perm2 = nullptr;      // (tile, bin)-sorted position -> caller's node id
     int32_t* d_bin_start = nullptr;  // ntiles * NQ + 1 absolute start positions
     bool have_bins = false;
+    int32_t* d_inv2 = nullptr;       // 1-D: inverse of perm2 (caller index -> position in the cell order), built on first use
+    bool have_inv2 = false;
+    int64_t cap_inv2 = 0;
     int bins_nq = 0;                 // NQ = 8 * S^3 bins per tile the table was built for
     int64_t cap_bins_nodes = 0, cap_bin_tab = 0;
     // fused spread + gather (lean.cu): work items expected at every output block (the items of its distinct neighbour

@@ -452,7 +452,7 @@ int nfftb200_destroy(nfftb200_plan* p)
     void* bufs[] = {p->d_hat_inv, p->d_poly, p->d_lin, p->d_grid, p->d_xs, p->d_tile_start, p->d_keys[0],
                     p->d_keys[1], p->d_vals[0], p->d_vals[1], p->d_hist, p->d_flag, p->d_stage_f,
                     p->d_stage_h, p->d_stage_k, p->d_stage_g, p->d_slab, p->d_tilebuf, p->d_items, p->d_tile_items,
-                    p->d_xs2, p->d_perm2, p->d_bin_start, p->d_expect, p->d_ready, p->d_pair_items, p->d_item_stride};
+                    p->d_xs2, p->d_perm2, p->d_bin_start, p->d_expect, p->d_ready, p->d_pair_items, p->d_item_stride, p->d_inv2};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 4; i++) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
     for (int i = 0; i < 6; i++) if (p->evk[i]) cudaEventDestroy(p->evk[i]);
@@ -470,6 +470,7 @@ int nfftb200_set_nodes(nfftb200_plan* p, const void* k, int64_t M, int where)
     if (p->timing) cudaEventRecord(p->ev[0], p->stream);
     p->have_nodes = false;
     p->have_bins = false;
+    p->have_inv2 = false;
     if (M > p->cap_nodes) {
         void* old[] = {p->d_xs, p->d_keys[0], p->d_keys[1], p->d_vals[0], p->d_vals[1]};
         for (void* b : old) if (b) cudaFree(b);
