@@ -82,6 +82,23 @@ def test_geometry_matches_init_params(nb, N, T, m, sigma):
     L.nfftb200_destroy(h)
 
 
+@pytest.mark.parametrize("T,m,B,want", [(np.float32, 4, 32, (16, 16)), (np.float32, 3, 8, (16, 16)), (np.float32, 4, 7, (64, 64)),
+                                        (np.float64, 4, 32, (64, 64)), (np.float32, 5, 32, (64, 64))])
+def test_default_tiles_of_batched_2d_plans(nb, T, m, B, want):
+    """the reference default is 64 x 64 (src/precomputation.jl:59-77); Float32 plans with ntransforms >= 8 and m <= 4 take
+    16 x 16 tiles so that the padded tiles of the whole batch fit one CTA's shared memory (csrc/twod_batch.cuh).  The
+    tile size only changes the reported blockSize and the permutation that goes with it (tests: bit-exact vs the oracle
+    built with the same blockSize)."""
+    L = nb.lib()
+    st, h = host_plan(nb, (512, 512), T, m, 2.0, B=B)
+    assert st == 0
+    Nt = (C.c_int64 * 2)(); bs = (C.c_int64 * 2)()
+    nt, lut, sg, M = C.c_int64(), C.c_int64(), C.c_double(), C.c_int64()
+    L.nfftb200_get_info(h, Nt, bs, C.byref(nt), C.byref(lut), C.byref(sg), C.byref(M))
+    assert tuple(bs) == want
+    L.nfftb200_destroy(h)
+
+
 def test_oversampled_size_uses_the_plan_precision(nb):
     """Ñ_d = (ceil(Int, σ*N_d) ÷ 2)*2 with σ::T (src/precomputation.jl:25-27): Float32 * Int is a Float32 product, so a
     Float32 plan with non-dyadic σ can get a different Ñ than the Float64 plan.  Pinned independently of the oracle by
