@@ -4,17 +4,19 @@
 //   (/root/reference/src/convolution.jl:229-492 applied to every slice of the batched arrays, NFFT.jl:mul! with dims).
 //
 // The per-transform kernels evaluate the 2 x 2m window taps of every node once per transform (32 times for C3) and
-// keep one padded tile in shared memory.  Here one CTA keeps the padded tile of BC = 8 * TPW transforms resident
-// (planes[t][y][x], 16 x 16 tiles: 24^2 cells x 32 transforms = 150 KB) and walks the tile's nodes ONCE:
-//   * a producer warp (warp 8) evaluates the taps of the next chunk of 64 nodes (lane per node), looks up the nodes'
-//     caller indices and -- adjoint -- gathers their BC coefficients, into the other half of a double buffer;
-//   * the 8 consumer warps each own TPW transforms; lane (i, t) owns tap column i of transform t.  Adjoint: 2m
-//     read-modify-writes of its plane per node (rows y), 64-byte contiguous per transform, the plane pitch chosen so that
-//     the four transforms of a warp fall on distinct banks.  Forward: 2m loads, a 3-stage shuffle sum over the columns.
-//     Warps never share a plane, so there are no conflicts to colour, no atomics, and the summation order is fixed;
-//   * adjoint: the planes go to the same per-(transform, work item) scratch layout k_gather_tiles2d reads.
-// Per (node, transform) this is ~10 issue slots and 16 shared-memory wavefronts instead of ~35 issue slots; the
-// adjoint is bound by the shared-memory read-modify-write bandwidth (2^20 nodes x 32 x 64 taps x 16 B = 34 GB).
+// keep one padded tile in shared memory.  Here one CTA keeps the padded tile of a whole group of transforms resident
+// (planes[t][y][x]; 16 x 16 tiles: 24^2 cells x 32 transforms = 150 KB) and walks the tile's nodes ONCE, warp-specialised:
+//   * producer warps evaluate the taps of the next chunk of 64 nodes (lane per node), look up the nodes' caller indices
+//     and -- adjoint -- gather the chunk's coefficients, into the other half of a double / triple buffer;
+//   * consumer warps own transforms, so warps never share a plane: nothing to colour, no atomics, fixed summation order.
+// What the launcher (twod.cu) uses:
+//   adjoint : k_spread_win2d    register windows (16 columns x 8 exact rows) over the plan-time bin order of
+//                               sort.cu: k_bin_order2d, 16 transforms per CTA, two CTAs per SM; the planes go to the
+//                               per-(transform, work item) scratch layout the 2-D gather kernels read
+//   forward : k_interp_batch2d  lane (tap column, transform), 8 nodes per halving butterfly, 32 / 16 / 8 transforms per CTA
+//   k_spread_batch2d            the first adjoint form (read-modify-write of the planes per node): kernel_mode 7 and tiles
+//                               the windows cannot take; kept because it is the simplest statement of the design
+// The measured sequence of forms is in DESIGN.md 3.6 and in the comments above each kernel.
 #pragma once
 
 constexpr int TB_NCH = 64;            // nodes per chunk
